@@ -1,0 +1,171 @@
+"""Host-side mirror of the reference's annealing interface over the C ABI.
+
+Python is only the driver for pytest and bench.py; the reference-facing host layer
+is the C++ shim in include/simulated_annealing/annealing.hpp.  Names and argument
+meaning follow /root/reference/include/simulated_annealing/annealing.hpp:55-58 and
+/root/reference/app/one-solver-anneal.cpp:23-39.
+"""
+import ctypes
+import math
+
+import numpy as np
+
+from . import capi
+
+
+def construct_linear_beta_schedule(beta_min, beta_max, num_iter):
+    """one-solver-anneal.cpp:23-29 (ends at beta_min + beta_max, a reference quirk)."""
+    return np.array([beta_min + beta_max * i / float(num_iter - 1) for i in range(num_iter)],
+                    dtype=np.float64)
+
+
+def construct_geometric_beta_schedule(beta_min, beta_max, num_iter):
+    """one-solver-anneal.cpp:31-39 (iterated product, not pow(alpha, i))."""
+    schedule = np.empty(num_iter, dtype=np.float64)
+    schedule[0] = beta_min
+    alpha = math.pow(beta_max / beta_min, 1.0 / (num_iter - 1))
+    for i in range(1, num_iter):
+        schedule[i] = schedule[i - 1] * alpha
+    return schedule
+
+
+class AnnealResult:
+    def __init__(self, state, energy, index, stats, best_energies=None, best_states_packed=None):
+        self.state = state            # uint8[N] (qubo::Solution::state)
+        self.energy = energy          # float   (qubo::Solution::energy)
+        self.index = index            # global id of the winning trajectory
+        self.stats = stats            # dict of osa_stats
+        self.best_energies = best_energies
+        self.best_states_packed = best_states_packed
+
+
+class Problem:
+    """Device-resident QUBO (dense flatten_qubo layout or CSR)."""
+
+    def __init__(self, handle, n):
+        self._h = handle
+        self.n = n
+        self.nw = (n + 31) // 32
+
+    @classmethod
+    def dense(cls, qsym, device=0, sweep_precision=capi.SWEEP_F64):
+        lib = capi.load()
+        q = np.ascontiguousarray(qsym)
+        if q.ndim != 2 or q.shape[0] != q.shape[1]:
+            raise ValueError("qsym must be a square matrix")
+        h = ctypes.c_void_p()
+        if q.dtype == np.float32:
+            capi.check(lib.osa_problem_create_dense_f32(q.ctypes.data, q.shape[0], device,
+                                                        ctypes.byref(h)))
+        else:
+            q = np.ascontiguousarray(q, dtype=np.float64)
+            capi.check(lib.osa_problem_create_dense_f64(q.ctypes.data, q.shape[0], device,
+                                                        sweep_precision, ctypes.byref(h)))
+        return cls(h, q.shape[0])
+
+    @classmethod
+    def csr(cls, rowptr, col, val, diag, device=0, sweep_precision=capi.SWEEP_F64):
+        lib = capi.load()
+        rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+        col = np.ascontiguousarray(col, dtype=np.int32)
+        val = np.ascontiguousarray(val, dtype=np.float64)
+        diag = np.ascontiguousarray(diag, dtype=np.float64)
+        n = diag.shape[0]
+        h = ctypes.c_void_p()
+        capi.check(lib.osa_problem_create_csr_f64(rowptr.ctypes.data, col.ctypes.data,
+                                                  val.ctypes.data, diag.ctypes.data, n, device,
+                                                  sweep_precision, ctypes.byref(h)))
+        return cls(h, n)
+
+    def close(self):
+        if self._h:
+            capi.load().osa_problem_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def anneal(self, beta_schedule, num_iter, num_tries, sweeps_per_beta=1, seed=1234,
+               first_try=0, mode=capi.MODE_RANDOM_SITE, accept_rule=capi.ACCEPT_REFERENCE,
+               kernel_variant=capi.KID_AUTO, want_energies=False, want_states=False):
+        """sa::anneal(instance, q, beta_schedule, num_iter, num_tries, sweeps_per_beta)."""
+        lib = capi.load()
+        sched = np.ascontiguousarray(beta_schedule, dtype=np.float64)
+        if sched.shape[0] < num_iter:
+            raise ValueError("beta_schedule shorter than num_iter")
+        prm = capi.AnnealParams(seed=seed, first_try=first_try, num_tries=num_tries,
+                                num_iter=num_iter, sweeps_per_beta=sweeps_per_beta, mode=mode,
+                                accept_rule=accept_rule, kernel_variant=kernel_variant, flags=0)
+        energies = np.empty(num_tries, dtype=np.float64) if want_energies else None
+        states = np.empty((num_tries, self.nw), dtype=np.uint32) if want_states else None
+        state = np.empty(self.n, dtype=np.uint8)
+        e = ctypes.c_double()
+        idx = ctypes.c_uint64()
+        st = capi.Stats()
+        capi.check(lib.osa_anneal(self._h, sched.ctypes.data, ctypes.byref(prm),
+                                  energies.ctypes.data if want_energies else None,
+                                  states.ctypes.data if want_states else None,
+                                  state.ctypes.data, ctypes.byref(e), ctypes.byref(idx),
+                                  ctypes.byref(st)))
+        return AnnealResult(state, e.value, idx.value, st.as_dict(), energies, states)
+
+    def energy_batch(self, states_packed):
+        """sa::energy (annealing.hpp:31-40) of packed states, evaluated on the device."""
+        lib = capi.load()
+        s = np.ascontiguousarray(states_packed, dtype=np.uint32)
+        if s.ndim == 1:
+            s = s.reshape(1, -1)
+        if s.shape[1] != self.nw:
+            raise ValueError("states_packed must have ceil(N/32) words per state")
+        out = np.empty(s.shape[0], dtype=np.float64)
+        capi.check(lib.osa_energy_batch(self._h, s.ctypes.data, s.shape[0], out.ctypes.data))
+        return out
+
+
+def device_count():
+    c = ctypes.c_int()
+    capi.check(capi.load().osa_device_count(ctypes.byref(c)))
+    return c.value
+
+
+def device_name(device=0):
+    buf = ctypes.create_string_buffer(256)
+    capi.check(capi.load().osa_device_name(device, buf, 256))
+    return buf.value.decode()
+
+
+def measure_read_bandwidth(nbytes, iters=20, device=0):
+    g = ctypes.c_double()
+    capi.check(capi.load().osa_measure_read_bandwidth(device, nbytes, iters, ctypes.byref(g)))
+    return g.value
+
+
+def pack_states(states01):
+    """[T][N] 0/1 -> [T][ceil(N/32)] uint32, bit i%32 of word i/32 = variable i."""
+    s = np.asarray(states01, dtype=np.uint8)
+    if s.ndim == 1:
+        s = s.reshape(1, -1)
+    t, n = s.shape
+    nw = (n + 31) // 32
+    padded = np.zeros((t, nw * 32), dtype=np.uint8)
+    padded[:, :n] = s
+    bits = padded.reshape(t, nw, 32).astype(np.uint64)
+    weights = (np.uint64(1) << np.arange(32, dtype=np.uint64))
+    return (bits * weights).sum(axis=2).astype(np.uint32)
+
+
+def unpack_states(packed, n):
+    p = np.asarray(packed, dtype=np.uint32)
+    if p.ndim == 1:
+        p = p.reshape(1, -1)
+    bits = (p[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & np.uint32(1)
+    return bits.reshape(p.shape[0], -1)[:, :n].astype(np.uint8)

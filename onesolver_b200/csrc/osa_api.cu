@@ -1,0 +1,668 @@
+// osa_api.cu -- the C ABI declared in include/onesolver_b200.h.
+//
+// Host orchestration of the annealing hot path: device-resident problem layouts
+// (replacing the sycl::buffer set-up of /root/reference/include/simulated_annealing/
+// annealing.hpp:59-72), kernel selection, the exact-energy epilogue and the argmin
+// (annealing.hpp:134-139).  No CPU compute path exists here: every failure to reach a
+// CUDA device is reported as an error.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "osa_common.cuh"
+
+using namespace osa;
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      int _code = (_e == cudaErrorNoDevice || _e == cudaErrorInsufficientDriver)             \
+                      ? OSA_ERR_NO_DEVICE                                                    \
+                      : (_e == cudaErrorMemoryAllocation ? OSA_ERR_NOMEM : OSA_ERR_CUDA);    \
+      return fail(_code, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,   \
+                  __LINE__);                                                                 \
+    }                                                                                        \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+// problem handle
+// ---------------------------------------------------------------------------
+struct osa_problem {
+  int device = 0;
+  int n = 0;
+  int nw = 0;
+  bool sparse = false;
+  int prec = OSA_SWEEP_F64;
+  // dense
+  size_t ld = 0;          // leading dimension of qoff (sweep precision)
+  size_t rows_pad = 0;    // rows allocated (multiple of 32)
+  void *d_qoff = nullptr; // zero-diagonal symmetric copy, sweep precision
+  void *d_diag = nullptr; // [ld] sweep precision
+  size_t ld64 = 0;
+  double *d_q64 = nullptr; // [n][ld64] original values incl. diagonal (exact energies)
+  // csr
+  int64_t nnz = 0;
+  int32_t *d_rowptr = nullptr, *d_col = nullptr;
+  void *d_val = nullptr;      // sweep precision
+  double *d_val64 = nullptr;
+  double *d_diag64 = nullptr;
+  // execution
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  // workspace (grow-only)
+  size_t cap_tries = 0;
+  double *d_best_rel = nullptr;
+  double *d_energy = nullptr;
+  uint32_t *d_states = nullptr;
+  size_t cap_states_words = 0;
+  uint32_t *d_xbest_ws = nullptr;
+  size_t cap_ws_words = 0;
+  void *d_tscale = nullptr;
+  size_t cap_tscale_bytes = 0;
+  Counters *d_counters = nullptr;
+  unsigned long long *d_arg_idx = nullptr;
+  double *d_arg_e = nullptr;
+};
+
+namespace {
+
+size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+// build the sweep-precision layouts from a dense upload
+template <typename TIn, typename T>
+__global__ void k_prep_dense(const TIn *__restrict__ in, int n, T *__restrict__ qoff, size_t ld,
+                             T *__restrict__ diag, double *__restrict__ q64, size_t ld64) {
+  const size_t total = (size_t)n * n;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / n), j = (int)(idx % n);
+    const TIn v = in[idx];
+    q64[(size_t)i * ld64 + j] = (double)v;
+    if (i == j) {
+      diag[i] = (T)v;
+    } else {
+      qoff[(size_t)i * ld + j] = (T)v;
+    }
+  }
+}
+
+template <typename TIn>
+__global__ void k_check_symmetric(const TIn *__restrict__ in, int n, int *__restrict__ bad) {
+  const size_t total = (size_t)n * n;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / n), j = (int)(idx % n);
+    if (j > i) {
+      const TIn a = in[idx], b = in[(size_t)j * n + i];
+      if (!(a == b)) atomicExch(bad, 1);
+    }
+  }
+}
+
+template <typename T>
+__global__ void k_convert(const double *__restrict__ in, T *__restrict__ out, size_t count) {
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < count;
+       idx += (size_t)gridDim.x * blockDim.x)
+    out[idx] = (T)in[idx];
+}
+
+int init_exec(osa_problem *p) {
+  CUDA_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  for (auto &e : p->ev) CUDA_TRY(cudaEventCreate(&e));
+  CUDA_TRY(cudaMalloc(&p->d_counters, sizeof(Counters)));
+  CUDA_TRY(cudaMalloc(&p->d_arg_idx, sizeof(unsigned long long)));
+  CUDA_TRY(cudaMalloc(&p->d_arg_e, sizeof(double)));
+  return OSA_OK;
+}
+
+int select_device(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(OSA_ERR_NO_DEVICE, "no CUDA device available: %s",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  if (device < 0 || device >= count)
+    return fail(OSA_ERR_INVALID, "device %d out of range [0, %d)", device, count);
+  CUDA_TRY(cudaSetDevice(device));
+  return OSA_OK;
+}
+
+template <typename TIn>
+int create_dense(const TIn *qsym, int n, int device, int prec, osa_problem **out) {
+  if (!qsym || !out) return fail(OSA_ERR_INVALID, "null argument");
+  if (n < 1) return fail(OSA_ERR_INVALID, "n must be >= 1 (got %d)", n);
+  if (prec != OSA_SWEEP_F64 && prec != OSA_SWEEP_F32)
+    return fail(OSA_ERR_INVALID, "unknown sweep precision %d", prec);
+  int rc = select_device(device);
+  if (rc) return rc;
+
+  osa_problem *p = new (std::nothrow) osa_problem();
+  if (!p) return fail(OSA_ERR_NOMEM, "out of host memory");
+  p->device = device;
+  p->n = n;
+  p->nw = (n + 31) / 32;
+  p->prec = prec;
+  auto bail = [&](int code) {
+    osa_problem_destroy(p);
+    return code;
+  };
+  rc = init_exec(p);
+  if (rc) return bail(rc);
+
+  const size_t esz = prec == OSA_SWEEP_F32 ? 4 : 8;
+  p->ld = round_up((size_t)n, prec == OSA_SWEEP_F32 ? 1024 : 512);
+  p->rows_pad = round_up((size_t)n, 32);
+  p->ld64 = round_up((size_t)n, 2);
+
+  TIn *d_in = nullptr;
+  int *d_bad = nullptr;
+#define TRY_B(expr)                                                                          \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      if (d_in) cudaFree(d_in);                                                              \
+      if (d_bad) cudaFree(d_bad);                                                            \
+      fail(_e == cudaErrorMemoryAllocation ? OSA_ERR_NOMEM : OSA_ERR_CUDA, "%s failed: %s",  \
+           #expr, cudaGetErrorString(_e));                                                   \
+      return bail(_e == cudaErrorMemoryAllocation ? OSA_ERR_NOMEM : OSA_ERR_CUDA);           \
+    }                                                                                        \
+  } while (0)
+
+  const size_t total = (size_t)n * n;
+  TRY_B(cudaMalloc(&d_in, total * sizeof(TIn)));
+  TRY_B(cudaMalloc(&d_bad, sizeof(int)));
+  TRY_B(cudaMalloc(&p->d_qoff, p->rows_pad * p->ld * esz));
+  TRY_B(cudaMalloc(&p->d_diag, p->ld * esz));
+  TRY_B(cudaMalloc(&p->d_q64, (size_t)n * p->ld64 * sizeof(double)));
+  TRY_B(cudaMemcpyAsync(d_in, qsym, total * sizeof(TIn), cudaMemcpyHostToDevice, p->stream));
+  TRY_B(cudaMemsetAsync(d_bad, 0, sizeof(int), p->stream));
+  TRY_B(cudaMemsetAsync(p->d_qoff, 0, p->rows_pad * p->ld * esz, p->stream));
+  TRY_B(cudaMemsetAsync(p->d_diag, 0, p->ld * esz, p->stream));
+  TRY_B(cudaMemsetAsync(p->d_q64, 0, (size_t)n * p->ld64 * sizeof(double), p->stream));
+  const int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  k_check_symmetric<TIn><<<grid, 256, 0, p->stream>>>(d_in, n, d_bad);
+  if (prec == OSA_SWEEP_F32)
+    k_prep_dense<TIn, float><<<grid, 256, 0, p->stream>>>(d_in, n, (float *)p->d_qoff, p->ld,
+                                                          (float *)p->d_diag, p->d_q64, p->ld64);
+  else
+    k_prep_dense<TIn, double><<<grid, 256, 0, p->stream>>>(d_in, n, (double *)p->d_qoff, p->ld,
+                                                           (double *)p->d_diag, p->d_q64, p->ld64);
+  TRY_B(cudaGetLastError());
+  int bad = 0;
+  TRY_B(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+  TRY_B(cudaStreamSynchronize(p->stream));
+  cudaFree(d_in);
+  cudaFree(d_bad);
+  d_in = nullptr;
+  d_bad = nullptr;
+#undef TRY_B
+  if (bad) {
+    fail(OSA_ERR_INVALID, "Q is not symmetric (expected helpers::flatten_qubo layout)");
+    return bail(OSA_ERR_INVALID);
+  }
+  *out = p;
+  return OSA_OK;
+}
+
+int ensure_workspace(osa_problem *p, uint64_t num_tries, int num_iter) {
+  if (num_tries > p->cap_tries) {
+    if (p->d_best_rel) cudaFree(p->d_best_rel);
+    if (p->d_energy) cudaFree(p->d_energy);
+    p->d_best_rel = nullptr;
+    p->d_energy = nullptr;
+    p->cap_tries = 0;
+    CUDA_TRY(cudaMalloc(&p->d_best_rel, num_tries * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&p->d_energy, num_tries * sizeof(double)));
+    p->cap_tries = num_tries;
+  }
+  const size_t words = (size_t)num_tries * p->nw;
+  if (words > p->cap_states_words) {
+    if (p->d_states) cudaFree(p->d_states);
+    p->d_states = nullptr;
+    p->cap_states_words = 0;
+    CUDA_TRY(cudaMalloc(&p->d_states, words * sizeof(uint32_t)));
+    p->cap_states_words = words;
+  }
+  if (p->sparse) {
+    const size_t ws = sparse_ws_words(p->n, num_tries);
+    if (ws > p->cap_ws_words) {
+      if (p->d_xbest_ws) cudaFree(p->d_xbest_ws);
+      p->d_xbest_ws = nullptr;
+      p->cap_ws_words = 0;
+      CUDA_TRY(cudaMalloc(&p->d_xbest_ws, ws * sizeof(uint32_t)));
+      p->cap_ws_words = ws;
+    }
+  }
+  const size_t tb = (size_t)num_iter * 8;
+  if (tb > p->cap_tscale_bytes) {
+    if (p->d_tscale) cudaFree(p->d_tscale);
+    p->d_tscale = nullptr;
+    p->cap_tscale_bytes = 0;
+    CUDA_TRY(cudaMalloc(&p->d_tscale, tb));
+    p->cap_tscale_bytes = tb;
+  }
+  return OSA_OK;
+}
+
+int exact_energies(osa_problem *p, const uint32_t *d_states, uint64_t count, double *d_out) {
+  if (p->sparse) {
+    CUDA_TRY(launch_energy_csr(p->d_rowptr, p->d_col, p->d_val64, p->d_diag64, p->n, d_states,
+                               p->nw, count, d_out, p->stream));
+  } else {
+    CUDA_TRY(launch_energy_dense(p->d_q64, p->ld64, p->n, d_states, p->nw, count, d_out,
+                                 p->stream));
+  }
+  return OSA_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int osa_abi_version(void) { return OSA_ABI_VERSION; }
+
+const char *osa_last_error(void) { return g_last_error.c_str(); }
+
+int osa_device_count(int *count) {
+  if (!count) return fail(OSA_ERR_INVALID, "null argument");
+  *count = 0;
+  cudaError_t e = cudaGetDeviceCount(count);
+  if (e != cudaSuccess) {
+    *count = 0;
+    return fail(OSA_ERR_NO_DEVICE, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+  }
+  return OSA_OK;
+}
+
+int osa_device_name(int device, char *buf, size_t buflen) {
+  if (!buf || buflen == 0) return fail(OSA_ERR_INVALID, "null argument");
+  int rc = select_device(device);
+  if (rc) return rc;
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  snprintf(buf, buflen, "%s", prop.name);
+  return OSA_OK;
+}
+
+const char *osa_kernel_name(int kernel_id) {
+  switch (kernel_id) {
+    case KID_DENSE_SEQ: return "dense_seq";
+    case KID_DENSE_GENERIC: return "dense_generic";
+    case KID_SPARSE: return "sparse_csr";
+    default: return "auto";
+  }
+}
+
+int osa_problem_create_dense_f64(const double *qsym, int n, int device, int sweep_precision,
+                                 osa_problem **out) {
+  return create_dense<double>(qsym, n, device, sweep_precision, out);
+}
+
+int osa_problem_create_dense_f32(const float *qsym, int n, int device, osa_problem **out) {
+  return create_dense<float>(qsym, n, device, OSA_SWEEP_F32, out);
+}
+
+int osa_problem_create_csr_f64(const int32_t *rowptr, const int32_t *col, const double *val,
+                               const double *diag, int n, int device, int sweep_precision,
+                               osa_problem **out) {
+  if (!rowptr || !diag || !out) return fail(OSA_ERR_INVALID, "null argument");
+  if (n < 1) return fail(OSA_ERR_INVALID, "n must be >= 1 (got %d)", n);
+  if (sweep_precision != OSA_SWEEP_F64 && sweep_precision != OSA_SWEEP_F32)
+    return fail(OSA_ERR_INVALID, "unknown sweep precision %d", sweep_precision);
+  if (rowptr[0] != 0) return fail(OSA_ERR_INVALID, "rowptr[0] must be 0");
+  const int64_t nnz = rowptr[n];
+  if (nnz < 0 || (nnz > 0 && (!col || !val))) return fail(OSA_ERR_INVALID, "bad CSR arrays");
+  if ((size_t)n * sizeof(uint32_t) > 227 * 1024)
+    return fail(OSA_ERR_UNSUPPORTED, "sparse kernel supports n <= %d", 227 * 1024 / 4);
+  for (int i = 0; i < n; ++i) {
+    if (rowptr[i + 1] < rowptr[i]) return fail(OSA_ERR_INVALID, "rowptr not monotone at %d", i);
+    for (int32_t q = rowptr[i]; q < rowptr[i + 1]; ++q) {
+      if (col[q] < 0 || col[q] >= n || col[q] == i)
+        return fail(OSA_ERR_INVALID, "row %d: bad column %d", i, col[q]);
+      if (q > rowptr[i] && col[q] <= col[q - 1])
+        return fail(OSA_ERR_INVALID, "row %d: columns must be strictly ascending", i);
+    }
+  }
+  int rc = select_device(device);
+  if (rc) return rc;
+  osa_problem *p = new (std::nothrow) osa_problem();
+  if (!p) return fail(OSA_ERR_NOMEM, "out of host memory");
+  p->device = device;
+  p->n = n;
+  p->nw = (n + 31) / 32;
+  p->sparse = true;
+  p->prec = sweep_precision;
+  p->nnz = nnz;
+  rc = init_exec(p);
+  if (rc) {
+    osa_problem_destroy(p);
+    return rc;
+  }
+  const size_t esz = sweep_precision == OSA_SWEEP_F32 ? 4 : 8;
+  const size_t nnz_a = (size_t)(nnz > 0 ? nnz : 1);
+  cudaError_t e = cudaSuccess;
+  auto step = [&](cudaError_t r) {
+    if (e == cudaSuccess) e = r;
+  };
+  step(cudaMalloc(&p->d_rowptr, (size_t)(n + 1) * sizeof(int32_t)));
+  step(cudaMalloc(&p->d_col, nnz_a * sizeof(int32_t)));
+  step(cudaMalloc(&p->d_val64, nnz_a * sizeof(double)));
+  step(cudaMalloc(&p->d_diag64, (size_t)n * sizeof(double)));
+  step(cudaMalloc(&p->d_val, (nnz_a + (size_t)n) * esz));
+  if (e == cudaSuccess) {
+    step(cudaMemcpyAsync(p->d_rowptr, rowptr, (size_t)(n + 1) * sizeof(int32_t),
+                         cudaMemcpyHostToDevice, p->stream));
+    if (nnz > 0) {
+      step(cudaMemcpyAsync(p->d_col, col, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice,
+                           p->stream));
+      step(cudaMemcpyAsync(p->d_val64, val, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice,
+                           p->stream));
+    }
+    step(cudaMemcpyAsync(p->d_diag64, diag, (size_t)n * sizeof(double), cudaMemcpyHostToDevice,
+                         p->stream));
+    // sweep-precision copies: val followed by diag in one allocation
+    if (sweep_precision == OSA_SWEEP_F32) {
+      if (nnz > 0) k_convert<float><<<64, 256, 0, p->stream>>>(p->d_val64, (float *)p->d_val, nnz);
+      k_convert<float><<<64, 256, 0, p->stream>>>(p->d_diag64, (float *)p->d_val + nnz_a, n);
+    } else {
+      if (nnz > 0)
+        k_convert<double><<<64, 256, 0, p->stream>>>(p->d_val64, (double *)p->d_val, nnz);
+      k_convert<double><<<64, 256, 0, p->stream>>>(p->d_diag64, (double *)p->d_val + nnz_a, n);
+    }
+    step(cudaGetLastError());
+    step(cudaStreamSynchronize(p->stream));
+  }
+  if (e != cudaSuccess) {
+    osa_problem_destroy(p);
+    return fail(e == cudaErrorMemoryAllocation ? OSA_ERR_NOMEM : OSA_ERR_CUDA,
+                "CSR upload failed: %s", cudaGetErrorString(e));
+  }
+  p->d_diag = (char *)p->d_val + nnz_a * esz;  // alias inside d_val; not freed separately
+  *out = p;
+  return OSA_OK;
+}
+
+int osa_problem_destroy(osa_problem *p) {
+  if (!p) return OSA_OK;
+  cudaSetDevice(p->device);
+  if (p->sparse) {
+    cudaFree(p->d_rowptr);
+    cudaFree(p->d_col);
+    cudaFree(p->d_val);
+    cudaFree(p->d_val64);
+    cudaFree(p->d_diag64);
+  } else {
+    cudaFree(p->d_qoff);
+    cudaFree(p->d_diag);
+    cudaFree(p->d_q64);
+  }
+  cudaFree(p->d_best_rel);
+  cudaFree(p->d_energy);
+  cudaFree(p->d_states);
+  cudaFree(p->d_xbest_ws);
+  cudaFree(p->d_tscale);
+  cudaFree(p->d_counters);
+  cudaFree(p->d_arg_idx);
+  cudaFree(p->d_arg_e);
+  for (auto &e : p->ev)
+    if (e) cudaEventDestroy(e);
+  if (p->stream) cudaStreamDestroy(p->stream);
+  delete p;
+  return OSA_OK;
+}
+
+int osa_problem_size(const osa_problem *p, int *n, int *is_sparse, int *sweep_precision) {
+  if (!p) return fail(OSA_ERR_INVALID, "null problem");
+  if (n) *n = p->n;
+  if (is_sparse) *is_sparse = p->sparse ? 1 : 0;
+  if (sweep_precision) *sweep_precision = p->prec;
+  return OSA_OK;
+}
+
+int osa_anneal(osa_problem *p, const double *beta_schedule, const osa_anneal_params *prm,
+               double *best_energies, uint32_t *best_states_packed, uint8_t *best_state,
+               double *best_energy, uint64_t *best_index, osa_stats *stats) {
+  if (!p || !beta_schedule || !prm) return fail(OSA_ERR_INVALID, "null argument");
+  if (prm->num_iter < 1) return fail(OSA_ERR_INVALID, "num_iter must be >= 1");
+  if (prm->sweeps_per_beta < 1) return fail(OSA_ERR_INVALID, "sweeps_per_beta must be >= 1");
+  if (prm->num_tries < 1) return fail(OSA_ERR_INVALID, "num_tries must be >= 1");
+  if (prm->mode != OSA_MODE_RANDOM_SITE && prm->mode != OSA_MODE_SEQUENTIAL_SWEEP)
+    return fail(OSA_ERR_INVALID, "unknown mode %d", prm->mode);
+  if (prm->flags != 0) return fail(OSA_ERR_INVALID, "unknown flags 0x%x", prm->flags);
+  if (prm->accept_rule != OSA_ACCEPT_REFERENCE && prm->accept_rule != OSA_ACCEPT_BOLTZMANN)
+    return fail(OSA_ERR_INVALID, "unknown accept rule %d", prm->accept_rule);
+  if ((uint64_t)prm->num_iter * (uint64_t)prm->sweeps_per_beta >= (1ull << 32))
+    return fail(OSA_ERR_INVALID, "num_iter * sweeps_per_beta must be < 2^32");
+  if (prm->first_try + prm->num_tries < prm->first_try ||
+      (prm->first_try + prm->num_tries) >> 62)
+    return fail(OSA_ERR_INVALID, "trajectory ids must stay below 2^62");
+  for (int i = 0; i < prm->num_iter; ++i)
+    if (!(beta_schedule[i] > 0.0) || !std::isfinite(beta_schedule[i]))
+      return fail(OSA_ERR_INVALID, "beta_schedule[%d] = %g is not a positive finite number", i,
+                  beta_schedule[i]);
+
+  int rc = select_device(p->device);
+  if (rc) return rc;
+  rc = ensure_workspace(p, prm->num_tries, prm->num_iter);
+  if (rc) return rc;
+
+  // threshold scale per iteration: accept iff dE < tscale * (-ln u)
+  const bool f32 = p->prec == OSA_SWEEP_F32;
+  std::vector<double> ts64(prm->num_iter);
+  std::vector<float> ts32(f32 ? prm->num_iter : 0);
+  for (int i = 0; i < prm->num_iter; ++i) {
+    ts64[i] = prm->accept_rule == OSA_ACCEPT_REFERENCE ? beta_schedule[i] : 1.0 / beta_schedule[i];
+    if (f32) ts32[i] = (float)ts64[i];
+  }
+  if (f32)
+    CUDA_TRY(cudaMemcpyAsync(p->d_tscale, ts32.data(), ts32.size() * sizeof(float),
+                             cudaMemcpyHostToDevice, p->stream));
+  else
+    CUDA_TRY(cudaMemcpyAsync(p->d_tscale, ts64.data(), ts64.size() * sizeof(double),
+                             cudaMemcpyHostToDevice, p->stream));
+  CUDA_TRY(cudaMemsetAsync(p->d_counters, 0, sizeof(Counters), p->stream));
+
+  int kid = prm->kernel_variant;
+  if (p->sparse) {
+    if (kid != KID_AUTO && kid != KID_SPARSE)
+      return fail(OSA_ERR_UNSUPPORTED, "kernel %d cannot run a CSR problem", kid);
+    kid = KID_SPARSE;
+  } else {
+    const int esz = f32 ? 4 : 8;
+    if (kid == KID_AUTO)
+      kid = (prm->mode == OSA_MODE_SEQUENTIAL_SWEEP && dense_seq_supported(p->n, esz))
+                ? KID_DENSE_SEQ
+                : KID_DENSE_GENERIC;
+    if (kid == KID_DENSE_SEQ &&
+        (prm->mode != OSA_MODE_SEQUENTIAL_SWEEP || !dense_seq_supported(p->n, esz)))
+      return fail(OSA_ERR_UNSUPPORTED, "dense_seq kernel needs sequential mode and n <= %d",
+                  f32 ? 8192 : 4096);
+    if (kid == KID_DENSE_GENERIC && !dense_generic_supported(p->n, esz))
+      return fail(OSA_ERR_UNSUPPORTED, "n = %d exceeds the shared-memory resident kernel", p->n);
+    if (kid != KID_DENSE_SEQ && kid != KID_DENSE_GENERIC)
+      return fail(OSA_ERR_UNSUPPORTED, "kernel %d cannot run a dense problem", kid);
+  }
+
+  LaunchInfo info = {0, 0, 0, 0};
+  int launches = 0;
+  CUDA_TRY(cudaEventRecord(p->ev[0], p->stream));
+  if (p->sparse) {
+    auto run = [&](auto tag) -> cudaError_t {
+      using T = decltype(tag);
+      SparseParams<T> sp;
+      sp.rowptr = p->d_rowptr;
+      sp.col = p->d_col;
+      sp.val = (const T *)p->d_val;
+      sp.diag = (const T *)p->d_diag;
+      sp.tscale = (const T *)p->d_tscale;
+      sp.n = p->n;
+      sp.num_iter = prm->num_iter;
+      sp.sweeps_per_beta = prm->sweeps_per_beta;
+      sp.mode = prm->mode;
+      sp.seed = prm->seed;
+      sp.first_try = prm->first_try;
+      sp.num_tries = prm->num_tries;
+      sp.best_rel = p->d_best_rel;
+      sp.best_states = p->d_states;
+      sp.xbest_ws = p->d_xbest_ws;
+      sp.nw = p->nw;
+      sp.counters = p->d_counters;
+      return launch_sparse<T>(sp, p->stream, &info);
+    };
+    CUDA_TRY(f32 ? run(float()) : run(double()));
+  } else {
+    auto run = [&](auto tag) -> cudaError_t {
+      using T = decltype(tag);
+      DenseParams<T> dp;
+      dp.qoff = (const T *)p->d_qoff;
+      dp.diag = (const T *)p->d_diag;
+      dp.tscale = (const T *)p->d_tscale;
+      dp.ld = p->ld;
+      dp.n = p->n;
+      dp.num_iter = prm->num_iter;
+      dp.sweeps_per_beta = prm->sweeps_per_beta;
+      dp.mode = prm->mode;
+      dp.seed = prm->seed;
+      dp.first_try = prm->first_try;
+      dp.num_tries = prm->num_tries;
+      dp.best_rel = p->d_best_rel;
+      dp.best_states = p->d_states;
+      dp.nw = p->nw;
+      dp.counters = p->d_counters;
+      return kid == KID_DENSE_SEQ ? launch_dense_seq<T>(dp, p->stream, &info)
+                                  : launch_dense_generic<T>(dp, p->stream, &info);
+    };
+    CUDA_TRY(f32 ? run(float()) : run(double()));
+  }
+  ++launches;
+  CUDA_TRY(cudaEventRecord(p->ev[1], p->stream));
+
+  // exact energies of the per-trajectory best states (annealing.hpp:125 semantics)
+  rc = exact_energies(p, p->d_states, prm->num_tries, p->d_energy);
+  if (rc) return rc;
+  ++launches;
+  CUDA_TRY(cudaEventRecord(p->ev[2], p->stream));
+  CUDA_TRY(launch_argmin(p->d_energy, prm->num_tries, p->d_arg_idx, p->d_arg_e, p->stream));
+  ++launches;
+  CUDA_TRY(cudaEventRecord(p->ev[3], p->stream));
+
+  unsigned long long h_idx = 0;
+  double h_e = 0.0;
+  Counters h_cnt;
+  CUDA_TRY(cudaMemcpyAsync(&h_idx, p->d_arg_idx, sizeof(h_idx), cudaMemcpyDeviceToHost, p->stream));
+  CUDA_TRY(cudaMemcpyAsync(&h_e, p->d_arg_e, sizeof(h_e), cudaMemcpyDeviceToHost, p->stream));
+  CUDA_TRY(cudaMemcpyAsync(&h_cnt, p->d_counters, sizeof(h_cnt), cudaMemcpyDeviceToHost, p->stream));
+  cudaError_t sync_err = cudaStreamSynchronize(p->stream);
+  if (sync_err != cudaSuccess)
+    return fail(OSA_ERR_CUDA, "annealing kernels failed: %s", cudaGetErrorString(sync_err));
+  if (h_idx >= prm->num_tries) return fail(OSA_ERR_CUDA, "argmin returned an invalid index");
+
+  if (best_energies)
+    CUDA_TRY(cudaMemcpyAsync(best_energies, p->d_energy, prm->num_tries * sizeof(double),
+                             cudaMemcpyDeviceToHost, p->stream));
+  if (best_states_packed)
+    CUDA_TRY(cudaMemcpyAsync(best_states_packed, p->d_states,
+                             (size_t)prm->num_tries * p->nw * sizeof(uint32_t),
+                             cudaMemcpyDeviceToHost, p->stream));
+  std::vector<uint32_t> win(p->nw);
+  CUDA_TRY(cudaMemcpyAsync(win.data(), p->d_states + (size_t)h_idx * p->nw,
+                           (size_t)p->nw * sizeof(uint32_t), cudaMemcpyDeviceToHost, p->stream));
+  CUDA_TRY(cudaStreamSynchronize(p->stream));
+  if (best_state)
+    for (int i = 0; i < p->n; ++i) best_state[i] = (uint8_t)((win[i >> 5] >> (i & 31)) & 1u);
+  if (best_energy) *best_energy = h_e;
+  if (best_index) *best_index = prm->first_try + h_idx;
+
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    const uint64_t per = (uint64_t)prm->num_iter * (uint64_t)prm->sweeps_per_beta *
+                         (prm->mode == OSA_MODE_SEQUENTIAL_SWEEP ? (uint64_t)p->n : 1ull);
+    stats->attempts = per * prm->num_tries;
+    stats->accepts = h_cnt.accepts;
+    stats->row_fetches = h_cnt.row_fetches;
+    stats->init_row_fetches = h_cnt.init_row_fetches;
+    cudaEventElapsedTime(&stats->ms_sweep, p->ev[0], p->ev[1]);
+    cudaEventElapsedTime(&stats->ms_energy, p->ev[1], p->ev[2]);
+    cudaEventElapsedTime(&stats->ms_reduce, p->ev[2], p->ev[3]);
+    cudaEventElapsedTime(&stats->ms_total, p->ev[0], p->ev[3]);
+    stats->kernel_id = kid;
+    stats->traj_per_batch = info.traj_per_batch;
+    stats->q_elem_bytes = f32 ? 4 : 8;
+    stats->grid = info.grid;
+    stats->launches = launches;
+  }
+  return OSA_OK;
+}
+
+int osa_energy_batch(osa_problem *p, const uint32_t *states_packed, uint64_t count, double *out) {
+  if (!p || !states_packed || !out) return fail(OSA_ERR_INVALID, "null argument");
+  if (count == 0) return OSA_OK;
+  int rc = select_device(p->device);
+  if (rc) return rc;
+  rc = ensure_workspace(p, count, 1);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(p->d_states, states_packed, (size_t)count * p->nw * sizeof(uint32_t),
+                           cudaMemcpyHostToDevice, p->stream));
+  rc = exact_energies(p, p->d_states, count, p->d_energy);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(out, p->d_energy, count * sizeof(double), cudaMemcpyDeviceToHost,
+                           p->stream));
+  CUDA_TRY(cudaStreamSynchronize(p->stream));
+  return OSA_OK;
+}
+
+int osa_measure_read_bandwidth(int device, size_t bytes, int iters, double *gbs) {
+  if (!gbs || bytes < 16 || iters < 1) return fail(OSA_ERR_INVALID, "bad argument");
+  int rc = select_device(device);
+  if (rc) return rc;
+  uint4 *buf = nullptr;
+  unsigned int *sink = nullptr;
+  cudaEvent_t a = nullptr, b = nullptr;
+  const size_t n_vec = bytes / 16;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  cudaError_t e = cudaMalloc(&buf, n_vec * 16);
+  if (e == cudaSuccess) e = cudaMalloc(&sink, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(buf, 1, n_vec * 16);
+  if (e == cudaSuccess) e = cudaEventCreate(&a);
+  if (e == cudaSuccess) e = cudaEventCreate(&b);
+  float ms = 0.f;
+  if (e == cudaSuccess) e = launch_read_bw(buf, n_vec, 2, sink, sms * 8, 0);  // warm L2
+  if (e == cudaSuccess) e = cudaEventRecord(a, 0);
+  if (e == cudaSuccess) e = launch_read_bw(buf, n_vec, iters, sink, sms * 8, 0);
+  if (e == cudaSuccess) e = cudaEventRecord(b, 0);
+  if (e == cudaSuccess) e = cudaEventSynchronize(b);
+  if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, a, b);
+  if (a) cudaEventDestroy(a);
+  if (b) cudaEventDestroy(b);
+  cudaFree(buf);
+  cudaFree(sink);
+  if (e != cudaSuccess) return fail(OSA_ERR_CUDA, "bandwidth probe failed: %s", cudaGetErrorString(e));
+  *gbs = (double)n_vec * 16.0 * iters / (ms * 1e-3) / 1e9;
+  return OSA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,206 @@
+// osa_common.cuh -- shared device helpers: Philox4x32-10, deterministic -ln(u),
+// rounding-explicit arithmetic, internal problem/launch structs.
+//
+// Every operation whose rounding matters for the bit-exact host replay goes
+// through det::fma / det::mul (explicit __f*_rn intrinsics, never contracted).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/onesolver_b200.h"
+
+namespace osa {
+
+// ---------------------------------------------------------------------------
+// RNG streams.  key = (seed lo, seed hi); ctr = (c0, c1, traj lo, traj hi | stream<<30)
+//   STREAM_INIT: c0 = j>>7, c1 = 0        -> word (j>>5)&3, bit j&31 = initial spin j
+//                (replaces random.bit(), reference annealing.hpp:90-92)
+//   STREAM_SEQ : c0 = site>>2, c1 = sweep -> word site&3 = uniform for (sweep, site)
+//   STREAM_RND : c0 = 0, c1 = step        -> word0 = site draw, word1 = uniform
+//                (replaces bit_index()/uniform(), reference annealing.hpp:101,108)
+// ---------------------------------------------------------------------------
+enum : uint32_t { STREAM_INIT = 0, STREAM_SEQ = 1, STREAM_RND = 2 };
+
+struct U4 { uint32_t x, y, z, w; };
+
+__device__ __forceinline__ U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                            uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0;
+    const uint32_t n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return U4{c0, c1, c2, c3};
+}
+
+__device__ __forceinline__ U4 engine_draw(uint64_t seed, uint64_t traj, uint32_t stream,
+                                          uint32_t c0, uint32_t c1) {
+  return philox4x32_10(c0, c1, (uint32_t)traj,
+                       ((uint32_t)(traj >> 32) & 0x3fffffffu) | (stream << 30), (uint32_t)seed,
+                       (uint32_t)(seed >> 32));
+}
+
+__device__ __forceinline__ uint32_t pick(const U4 &v, uint32_t i) {
+  return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
+}
+
+// -ln(u), u = (2w+1)/2^33 in (0,1).  24-bit truncated mantissa + the classic
+// single-precision minimax polynomial for ln(1+f); explicit rn intrinsics only.
+__device__ __forceinline__ float neglogf_det(uint32_t w) {
+  const uint64_t v = ((uint64_t)w << 1) | 1ull;
+  const int p = 63 - __clzll((long long)v);
+  const uint32_t m24 = (uint32_t)((v << (63 - p)) >> 40);
+  int e = p - 33;
+  float mf = __fmul_rn(__uint2float_rn(m24), 1.1920928955078125e-07f);  // * 2^-23 (exact)
+  if (m24 > 0x00B504F3u) {
+    mf = __fmul_rn(mf, 0.5f);
+    e += 1;
+  }
+  const float f = __fsub_rn(mf, 1.0f);
+  const float z = __fmul_rn(f, f);
+  float y = 7.0376836292E-2f;
+  y = __fmaf_rn(y, f, -1.1514610310E-1f);
+  y = __fmaf_rn(y, f, 1.1676998740E-1f);
+  y = __fmaf_rn(y, f, -1.2420140846E-1f);
+  y = __fmaf_rn(y, f, 1.4249322787E-1f);
+  y = __fmaf_rn(y, f, -1.6668057665E-1f);
+  y = __fmaf_rn(y, f, 2.0000714765E-1f);
+  y = __fmaf_rn(y, f, -2.4999993993E-1f);
+  y = __fmaf_rn(y, f, 3.3333331174E-1f);
+  y = __fmul_rn(y, f);
+  y = __fmul_rn(y, z);
+  const float fe = __int2float_rn(e);
+  y = __fmaf_rn(fe, -2.12194440e-4f, y);
+  y = __fmaf_rn(-0.5f, z, y);
+  float r = __fadd_rn(f, y);
+  r = __fmaf_rn(fe, 0.693359375f, r);
+  return -r;
+}
+
+namespace det {
+__device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+__device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+}  // namespace det
+
+// threshold theta = tscale * (T)(-ln u)
+template <typename T>
+__device__ __forceinline__ T threshold(T ts, uint32_t w) {
+  return det::mul(ts, (T)neglogf_det(w));
+}
+
+// 16-byte vector type per element type
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+  using type = float4;
+  static constexpr int V = 4;
+};
+template <> struct Vec16<double> {
+  using type = double2;
+  static constexpr int V = 2;
+};
+
+template <typename T>
+__device__ __forceinline__ void vec_unpack(const typename Vec16<T>::type &v, T *out);
+template <>
+__device__ __forceinline__ void vec_unpack<float>(const float4 &v, float *o) {
+  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+template <>
+__device__ __forceinline__ void vec_unpack<double>(const double2 &v, double *o) {
+  o[0] = v.x; o[1] = v.y;
+}
+
+// ---------------------------------------------------------------------------
+// launch parameter blocks (host fills, kernels read)
+// ---------------------------------------------------------------------------
+struct Counters {  // device-side accumulators, one struct per call
+  unsigned long long accepts;
+  unsigned long long row_fetches;
+  unsigned long long init_row_fetches;
+  unsigned long long pad;
+};
+
+template <typename T>
+struct DenseParams {
+  const T *qoff;   // [n_rows_pad][ld], zero diagonal, symmetric, zero padded
+  const T *diag;   // [ld], zero padded
+  const T *tscale; // [num_iter]
+  size_t ld;
+  int n;
+  int num_iter;
+  int sweeps_per_beta;
+  int mode;
+  uint64_t seed;
+  uint64_t first_try;
+  uint64_t num_tries;
+  double *best_rel;         // [num_tries]
+  uint32_t *best_states;    // [num_tries][nw]
+  int nw;                   // words per state = ceil(n/32)
+  Counters *counters;
+};
+
+template <typename T>
+struct SparseParams {
+  const int32_t *rowptr;
+  const int32_t *col;
+  const T *val;
+  const T *diag;
+  const T *tscale;
+  int n;
+  int num_iter;
+  int sweeps_per_beta;
+  int mode;
+  uint64_t seed;
+  uint64_t first_try;
+  uint64_t num_tries;
+  double *best_rel;
+  uint32_t *best_states;  // [num_tries][nw]
+  uint32_t *xbest_ws;     // [n_warps_total][n] transposed best-state workspace
+  int nw;
+  Counters *counters;
+};
+
+// kernel ids reported in osa_stats.kernel_id
+enum KernelId : int {
+  KID_AUTO = 0,
+  KID_DENSE_SEQ = 1,      // CTA-per-batch sequential sweep, h in registers
+  KID_DENSE_GENERIC = 2,  // warp-per-trajectory, h in shared memory (both modes)
+  KID_SPARSE = 3          // lane-per-trajectory CSR kernel (both modes)
+};
+
+// launchers implemented in the per-kernel .cu files; all return cudaError_t
+struct LaunchInfo { int grid; int block; int traj_per_batch; size_t smem; };
+
+template <typename T>
+cudaError_t launch_dense_seq(const DenseParams<T> &p, cudaStream_t s, LaunchInfo *info);
+template <typename T>
+cudaError_t launch_dense_generic(const DenseParams<T> &p, cudaStream_t s, LaunchInfo *info);
+template <typename T>
+cudaError_t launch_sparse(const SparseParams<T> &p, cudaStream_t s, LaunchInfo *info);
+bool dense_seq_supported(int n, int elem_bytes);
+bool dense_generic_supported(int n, int elem_bytes);
+size_t sparse_ws_words(int n, uint64_t num_tries);
+
+// exact fp64 energies (reference formula) of packed states
+cudaError_t launch_energy_dense(const double *q64, size_t ld64, int n, const uint32_t *states,
+                                int nw, uint64_t count, double *out, cudaStream_t s);
+cudaError_t launch_energy_csr(const int32_t *rowptr, const int32_t *col, const double *val64,
+                              const double *diag64, int n, const uint32_t *states, int nw,
+                              uint64_t count, double *out, cudaStream_t s);
+// argmin with lowest-index tie break; result: out_idx[0] = local index, out_e[0] = energy
+cudaError_t launch_argmin(const double *e, uint64_t count, unsigned long long *out_idx,
+                          double *out_e, cudaStream_t s);
+cudaError_t launch_read_bw(const uint4 *buf, size_t n_vec, int iters, unsigned int *sink,
+                           int grid, cudaStream_t s);
+
+}  // namespace osa

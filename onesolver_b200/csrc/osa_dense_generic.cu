@@ -1,0 +1,209 @@
+// osa_dense_generic.cu -- K1r: warp-per-trajectory dense annealing kernel (sm_100a).
+//
+// Covers the reference-faithful RANDOM-SITE mode (one attempt per (iter, sweep) at a
+// site drawn from the trajectory's own stream, /root/reference/include/
+// simulated_annealing/annealing.hpp:97-101) and is the catch-all for the sequential
+// mode when N exceeds the register-resident kernel (osa_dense_seq.cu).
+//
+// One warp owns one trajectory: local field h[N] and the bit-packed state live in
+// shared memory.  Attempts are evaluated 32 at a time (one per lane: site and
+// threshold come from the counter-based stream, so they are known up front); the warp
+// then walks from accepted flip to accepted flip (ballot/ffs), re-evaluating the
+// remaining lanes after every accepted flip, which reproduces the sequential chain
+// exactly.  An accepted flip streams row k of Q (coalesced 16-byte loads) into h.
+#include "osa_common.cuh"
+
+namespace osa {
+
+namespace {
+
+template <typename T>
+__global__ void k_dense_generic(const DenseParams<T> p, int n_pad, int per_warp_bytes) {
+  using VecT = typename Vec16<T>::type;
+  constexpr int V = Vec16<T>::V;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const uint64_t tl = (uint64_t)blockIdx.x * wpb + warp;
+  if (tl >= p.num_tries) return;  // whole warp leaves; no block-level barrier is used below
+  const uint64_t traj = p.first_try + tl;
+  const int n = p.n, nw = p.nw;
+
+  unsigned char *mine = smem_raw + (size_t)warp * per_warp_bytes;
+  T *h = reinterpret_cast<T *>(mine);
+  uint32_t *x = reinterpret_cast<uint32_t *>(mine + (size_t)n_pad * sizeof(T));
+  uint32_t *xb = x + nw;
+
+  // initial spins (replaces random.bit(), annealing.hpp:90-92)
+  for (int k = lane; k < nw; k += 32) {
+    const U4 d = engine_draw(p.seed, traj, STREAM_INIT, (uint32_t)k >> 2, 0u);
+    uint32_t word = pick(d, (uint32_t)k & 3u);
+    const int valid = n - k * 32;
+    if (valid < 32) word &= (1u << valid) - 1u;
+    x[k] = word;
+    xb[k] = word;
+  }
+  for (int j = lane * V; j < n_pad; j += 32 * V)
+    *reinterpret_cast<VecT *>(h + j) = *reinterpret_cast<const VecT *>(p.diag + j);
+  __syncwarp();
+
+  auto add_row = [&](int k, T sgn) {
+    const T *row = p.qoff + (size_t)k * p.ld;
+    for (int j = lane * V; j < n_pad; j += 32 * V) {
+      const VecT q = __ldg(reinterpret_cast<const VecT *>(row + j));
+      T qv[V], hv[V];
+      vec_unpack<T>(q, qv);
+      vec_unpack<T>(*reinterpret_cast<const VecT *>(h + j), hv);
+#pragma unroll
+      for (int e = 0; e < V; ++e) h[j + e] = det::fma(sgn, qv[e], hv[e]);
+    }
+  };
+
+  // initial local field: diag + rows of the set spins, in site order
+  unsigned long long cnt_init = 0, cnt_acc = 0;
+  for (int i = 0; i < n; ++i) {
+    if ((x[i >> 5] >> (i & 31)) & 1u) {
+      add_row(i, (T)1);
+      ++cnt_init;
+    }
+  }
+  __syncwarp();
+
+  double erel = 0.0, best = 0.0;
+  bool at_best = true;
+
+  // walk one batch of <=32 attempts (lane l: site_l, theta_l, active)
+  auto run_batch = [&](int site_l, T theta_l, bool active) {
+    uint32_t from = 0xffffffffu;
+    for (;;) {
+      __syncwarp();
+      uint32_t xl = 0;
+      T dEl = (T)0;
+      bool al = false;
+      if (active) {
+        xl = (x[site_l >> 5] >> (site_l & 31)) & 1u;
+        const T hl = h[site_l];
+        dEl = xl ? -hl : hl;
+        al = dEl < theta_l;
+      }
+      const uint32_t bal = __ballot_sync(0xffffffffu, al) & from;
+      if (bal == 0) break;
+      const int s = __ffs(bal) - 1;
+      const int k = __shfl_sync(0xffffffffu, site_l, s);
+      const T dEs = __shfl_sync(0xffffffffu, dEl, s);
+      const uint32_t xk = __shfl_sync(0xffffffffu, xl, s);
+      const double e = det::add(erel, (double)dEs);
+      erel = e;
+      if (e < best) {
+        best = e;
+        at_best = true;
+      } else if (at_best) {
+        for (int kk = lane; kk < nw; kk += 32) xb[kk] = x[kk];  // state before this flip
+        at_best = false;
+      }
+      __syncwarp();
+      if (lane == 0) x[k >> 5] ^= (1u << (k & 31));
+      add_row(k, xk ? (T)-1 : (T)1);
+      ++cnt_acc;
+      from = (s == 31) ? 0u : (0xffffffffu << (s + 1));
+    }
+  };
+
+  if (p.mode == OSA_MODE_SEQUENTIAL_SWEEP) {
+    uint32_t step = 0;
+    for (int iter = 0; iter < p.num_iter; ++iter) {
+      const T ts = p.tscale[iter];
+      for (int sw = 0; sw < p.sweeps_per_beta; ++sw, ++step) {
+        for (int i0 = 0; i0 < n; i0 += 32) {
+          const int site = i0 + lane;
+          const U4 d = engine_draw(p.seed, traj, STREAM_SEQ, (uint32_t)site >> 2, step);
+          const T theta = threshold<T>(ts, pick(d, (uint32_t)site & 3u));
+          run_batch(site, theta, site < n);
+        }
+      }
+    }
+  } else {
+    const uint64_t total = (uint64_t)p.num_iter * (uint64_t)p.sweeps_per_beta;
+    for (uint64_t s0 = 0; s0 < total; s0 += 32) {
+      const uint64_t st = s0 + lane;
+      const bool active = st < total;
+      int site = 0;
+      T theta = (T)0;
+      if (active) {
+        const int iter = (int)(st / (uint64_t)p.sweeps_per_beta);
+        const T ts = p.tscale[iter];
+        const U4 d = engine_draw(p.seed, traj, STREAM_RND, 0u, (uint32_t)st);
+        site = (int)__umulhi(d.x, (uint32_t)n);  // bit_index(), annealing.hpp:101
+        theta = threshold<T>(ts, d.y);
+      }
+      run_batch(site, theta, active);
+    }
+  }
+
+  __syncwarp();
+  if (at_best)
+    for (int k = lane; k < nw; k += 32) xb[k] = x[k];
+  __syncwarp();
+  for (int k = lane; k < nw; k += 32) p.best_states[tl * (uint64_t)nw + k] = xb[k];
+  if (lane == 0) {
+    p.best_rel[tl] = best;
+    atomicAdd(&p.counters->accepts, cnt_acc);
+    atomicAdd(&p.counters->row_fetches, cnt_acc);
+    atomicAdd(&p.counters->init_row_fetches, cnt_init);
+  }
+}
+
+constexpr size_t kMaxSmem = 227 * 1024;
+
+template <typename T>
+size_t per_warp_bytes(int n) {
+  constexpr int V = Vec16<T>::V;
+  const size_t n_pad = ((size_t)n + V - 1) / V * V;
+  const size_t nw = ((size_t)n + 31) / 32;
+  size_t b = n_pad * sizeof(T) + 2 * nw * sizeof(uint32_t);
+  return (b + 15) / 16 * 16;
+}
+
+template <typename T>
+cudaError_t launch_impl(const DenseParams<T> &p, cudaStream_t s, LaunchInfo *info) {
+  constexpr int V = Vec16<T>::V;
+  const size_t pw = per_warp_bytes<T>(p.n);
+  if (pw > kMaxSmem) return cudaErrorInvalidValue;
+  int wpb = (int)(kMaxSmem / pw);
+  if (wpb > 4) wpb = 4;  // several small CTAs per SM beat one big one for tiny N
+  const size_t smem = pw * (size_t)wpb;
+  cudaError_t err = cudaFuncSetAttribute(k_dense_generic<T>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  const uint64_t grid64 = (p.num_tries + wpb - 1) / wpb;
+  if (grid64 == 0 || grid64 > 0x7fffffffull) return cudaErrorInvalidValue;
+  const int n_pad = (p.n + V - 1) / V * V;
+  k_dense_generic<T><<<(unsigned)grid64, wpb * 32, smem, s>>>(p, n_pad, (int)pw);
+  if (info) {
+    info->grid = (int)grid64;
+    info->block = wpb * 32;
+    info->traj_per_batch = 1;
+    info->smem = smem;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+bool dense_generic_supported(int n, int elem_bytes) {
+  if (n < 1) return false;
+  return (elem_bytes == 4 ? per_warp_bytes<float>(n) : per_warp_bytes<double>(n)) <= kMaxSmem;
+}
+
+template <>
+cudaError_t launch_dense_generic<float>(const DenseParams<float> &p, cudaStream_t s,
+                                        LaunchInfo *info) {
+  return launch_impl<float>(p, s, info);
+}
+template <>
+cudaError_t launch_dense_generic<double>(const DenseParams<double> &p, cudaStream_t s,
+                                         LaunchInfo *info) {
+  return launch_impl<double>(p, s, info);
+}
+
+}  // namespace osa

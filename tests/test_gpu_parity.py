@@ -1,0 +1,218 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA engine, called through
+the C ABI, against the oracle (oracle/osa_oracle.c) on the same seeded inputs.
+
+Bars: spin sequences / best states bit-exact vs the host replay; returned energies
+equal to the reference energy function (annealing.hpp:31-40) to 1e-9 relative (fp64);
+best state == exhaustive ground state for N <= 30.
+"""
+import numpy as np
+import pytest
+
+from onesolver_b200 import Problem, capi, pack_states, unpack_states
+from onesolver_b200 import problems as gen
+from oracle import binding as ob
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-9  # north_star tolerance for fp64 energies
+
+
+def geo(num_iter, lo=0.1, hi=1.0):
+    return ob.ref_schedule("geometric", lo, hi, num_iter)
+
+
+def assert_states_equal(got, want, what):
+    bad = np.nonzero((got != want).any(axis=1))[0]
+    assert bad.size == 0, f"{what}: {bad.size}/{got.shape[0]} trajectories differ, first {bad[:8]}"
+
+
+def run_and_compare_dense(q, sched, num_iter, num_tries, mode, dtype, spb=1, kernel=capi.KID_AUTO,
+                          accept_rule=capi.ACCEPT_REFERENCE, first_try=0, seed=1234):
+    prec = capi.SWEEP_F32 if dtype == np.float32 else capi.SWEEP_F64
+    with Problem.dense(q, sweep_precision=prec) as prob:
+        res = prob.anneal(sched, num_iter, num_tries, sweeps_per_beta=spb, mode=mode,
+                          accept_rule=accept_rule, kernel_variant=kernel, first_try=first_try,
+                          seed=seed, want_energies=True, want_states=True)
+    r = res.stats["traj_per_batch"]
+    best_rel, best, _, cnt = ob.replay_dense(q, sched, num_iter, num_tries, sweeps_per_beta=spb,
+                                             mode=mode, accept_rule=accept_rule, seed=seed,
+                                             first_try=first_try, dtype=dtype, batch_r=r)
+    assert_states_equal(res.best_states_packed, best, "best states vs host replay")
+    assert res.stats["accepts"] == cnt.accepts
+    assert res.stats["attempts"] == cnt.attempts
+    assert res.stats["row_fetches"] == cnt.row_fetches
+    e_ref = ob.energy_packed(q, best)
+    np.testing.assert_allclose(res.best_energies, e_ref, rtol=REL, atol=1e-12)
+    k = int(np.argmin(e_ref))  # first minimum, like std::min_element
+    assert res.index == first_try + k
+    assert abs(res.energy - e_ref[k]) <= REL * max(1.0, abs(e_ref[k]))
+    np.testing.assert_array_equal(res.state, unpack_states(best[k], q.shape[0])[0])
+    return res, cnt
+
+
+# ---------------------------------------------------------------- config 1 / 2
+def test_config1_test1_qubo_defaults(gpu):
+    """BASELINE config 1 on the GPU: test1.qubo, 100 iters x 100 tries, geometric 0.1->1.0."""
+    lin = {0: -5, 1: -3, 2: -8, 3: -6}
+    quad = {(0, 1): 2, (0, 2): 4, (0, 3): 0, (1, 2): 1, (1, 3): 0, (2, 3): 5}
+    q = ob.ref_flatten(4, lin, quad).reshape(4, 4)
+    res, _ = run_and_compare_dense(q, geo(100), 100, 100, capi.MODE_RANDOM_SITE, np.float64)
+    assert res.energy == -12.0
+    np.testing.assert_array_equal(res.state, [1, 1, 0, 1])
+    # trajectory-level agreement with the reference-faithful restatement (exact arithmetic)
+    _, _, e_ref = ob.ref_anneal(q, 4, geo(100), 100, 100)
+    assert (res.best_energies == e_ref).mean() >= 0.99
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_config2_n24_matches_exhaustive_and_reference(gpu, dtype):
+    """BASELINE config 2: dense N=24, 4096 tries, best state == exhaustive ground state."""
+    n = 24
+    q = gen.dense_integer_qubo(n, seed=2026)
+    sched = geo(400, 0.5, 20.0)
+    res, _ = run_and_compare_dense(q, sched, 400, 4096, capi.MODE_RANDOM_SITE, dtype)
+    gs_state, gs_energy = ob.ref_exhaustive(q, n, num_ranges=8)
+    assert res.energy == gs_energy
+    assert ob.ref_energy(q, res.state.astype(np.int8)) == gs_energy
+    # ground-state hit probability vs the reference-faithful loop (same streams)
+    _, _, e_ref = ob.ref_anneal(q, n, sched, 400, 4096)
+    p_gpu = (res.best_energies == gs_energy).mean()
+    p_ref = (e_ref == gs_energy).mean()
+    ci = 3.0 * np.sqrt(max(p_ref * (1 - p_ref), 1e-4) / 4096) * np.sqrt(2)
+    assert abs(p_gpu - p_ref) <= ci, (p_gpu, p_ref, ci)
+    assert (res.best_energies == e_ref).mean() >= 0.98
+
+
+def test_n24_fractional_coefficients(gpu):
+    n = 24
+    q = gen.dense_uniform_qubo(n, seed=7)
+    res, _ = run_and_compare_dense(q, geo(300, 0.05, 2.0), 300, 2048, capi.MODE_RANDOM_SITE,
+                                   np.float64)
+    _, gs_energy = ob.ref_exhaustive(q, n, num_ranges=5)
+    assert abs(res.energy - gs_energy) <= REL * abs(gs_energy)
+
+
+# ---------------------------------------------------------------- dense, sequential sweeps
+@pytest.mark.parametrize("n,dtype,tries,sweeps", [
+    (5, np.float64, 20, 6), (33, np.float32, 40, 5), (64, np.float64, 33, 4),
+    (100, np.float32, 50, 4), (300, np.float64, 40, 3), (513, np.float64, 20, 2),
+    (1024, np.float32, 24, 2), (1100, np.float32, 17, 2), (1024, np.float64, 16, 2),
+    (2100, np.float32, 9, 1), (2048, np.float64, 9, 1), (4096, np.float32, 8, 1),
+])
+def test_dense_seq_bit_exact(gpu, n, dtype, tries, sweeps):
+    q = gen.dense_uniform_qubo(n, seed=100 + n)
+    scale = np.sqrt(n)
+    sched = geo(sweeps, 0.02 * scale, 0.6 * scale)
+    res, cnt = run_and_compare_dense(q, sched, sweeps, tries, capi.MODE_SEQUENTIAL_SWEEP, dtype)
+    assert res.stats["kernel_id"] == capi.KID_DENSE_SEQ
+    assert cnt.accepts > 0
+
+
+def test_dense_seq_sweeps_per_beta_and_boltzmann(gpu):
+    q = gen.dense_uniform_qubo(200, seed=5)
+    sched = ob.ref_schedule("linear", 0.05, 2.0, 4)
+    run_and_compare_dense(q, sched, 4, 30, capi.MODE_SEQUENTIAL_SWEEP, np.float32, spb=3,
+                          accept_rule=capi.ACCEPT_BOLTZMANN)
+
+
+@pytest.mark.parametrize("mode", [capi.MODE_RANDOM_SITE, capi.MODE_SEQUENTIAL_SWEEP])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_dense_generic_kernel_bit_exact(gpu, mode, dtype):
+    n = 150
+    q = gen.dense_uniform_qubo(n, seed=11)
+    iters = 3 if mode == capi.MODE_SEQUENTIAL_SWEEP else 700
+    sched = geo(iters, 0.3, 6.0)
+    res, _ = run_and_compare_dense(q, sched, iters, 37, mode, dtype, kernel=capi.KID_DENSE_GENERIC)
+    assert res.stats["kernel_id"] == capi.KID_DENSE_GENERIC
+
+
+def test_sharding_by_first_try_is_exact(gpu):
+    """Global trajectory ids key the RNG: shards reproduce the unsharded run (multi-GPU row)."""
+    q = gen.dense_uniform_qubo(96, seed=3)
+    sched = geo(3, 0.3, 4.0)
+    with Problem.dense(q, sweep_precision=capi.SWEEP_F32) as prob:
+        full = prob.anneal(sched, 3, 50, mode=capi.MODE_SEQUENTIAL_SWEEP, want_energies=True,
+                           want_states=True)
+        a = prob.anneal(sched, 3, 21, mode=capi.MODE_SEQUENTIAL_SWEEP, want_energies=True,
+                        want_states=True)
+        b = prob.anneal(sched, 3, 29, first_try=21, mode=capi.MODE_SEQUENTIAL_SWEEP,
+                        want_energies=True, want_states=True)
+        again = prob.anneal(sched, 3, 50, mode=capi.MODE_SEQUENTIAL_SWEEP, want_energies=True,
+                            want_states=True)
+    np.testing.assert_array_equal(np.vstack([a.best_states_packed, b.best_states_packed]),
+                                  full.best_states_packed)
+    np.testing.assert_array_equal(np.concatenate([a.best_energies, b.best_energies]),
+                                  full.best_energies)
+    np.testing.assert_array_equal(again.best_states_packed, full.best_states_packed)  # determinism
+    k = min((a, b), key=lambda r: (r.energy, r.index))
+    assert (k.energy, k.index) == (full.energy, full.index)
+
+
+# ---------------------------------------------------------------- sparse CSR
+@pytest.mark.parametrize("n,deg,dtype,mode,tries", [
+    (128, 6, np.float64, capi.MODE_SEQUENTIAL_SWEEP, 70),
+    (128, 6, np.float32, capi.MODE_RANDOM_SITE, 45),
+    (517, 15, np.float32, capi.MODE_SEQUENTIAL_SWEEP, 100),
+    (517, 15, np.float64, capi.MODE_RANDOM_SITE, 64),
+])
+def test_sparse_bit_exact(gpu, n, deg, dtype, mode, tries):
+    rowptr, col, val, diag = gen.sparse_random_graph(n, deg, seed=n + deg)
+    iters = 5 if mode == capi.MODE_SEQUENTIAL_SWEEP else 2000
+    sched = geo(iters, 0.05, 1.5)
+    prec = capi.SWEEP_F32 if dtype == np.float32 else capi.SWEEP_F64
+    with Problem.csr(rowptr, col, val, diag, sweep_precision=prec) as prob:
+        res = prob.anneal(sched, iters, tries, mode=mode, want_energies=True, want_states=True)
+    best_rel, best, _, cnt = ob.replay_csr(rowptr, col, val, diag, sched, iters, tries, mode=mode,
+                                           dtype=dtype)
+    assert res.stats["kernel_id"] == capi.KID_SPARSE
+    assert_states_equal(res.best_states_packed, best, "sparse best states vs host replay")
+    assert res.stats["accepts"] == cnt.accepts
+    q = gen.csr_to_dense(rowptr, col, val, diag)
+    e_ref = ob.energy_packed(q, best)
+    np.testing.assert_allclose(res.best_energies, e_ref, rtol=REL, atol=1e-12)
+    k = int(np.argmin(e_ref))
+    assert res.index == k and abs(res.energy - e_ref[k]) <= REL * max(1.0, abs(e_ref[k]))
+
+
+def test_sparse_equals_dense_engine_on_integer_instance(gpu):
+    """Same instance through the CSR and the dense kernels: with integer coefficients every
+    partial sum is exact, so both layouts must walk identical trajectories."""
+    rowptr, col, val, diag = gen.sparse_random_graph(96, 5, seed=9, integer=True)
+    q = gen.csr_to_dense(rowptr, col, val, diag)
+    sched = geo(4, 0.5, 8.0)
+    with Problem.csr(rowptr, col, val, diag) as ps, Problem.dense(q) as pd:
+        a = ps.anneal(sched, 4, 64, mode=capi.MODE_SEQUENTIAL_SWEEP, want_states=True)
+        b = pd.anneal(sched, 4, 64, mode=capi.MODE_SEQUENTIAL_SWEEP, want_states=True)
+    np.testing.assert_array_equal(a.best_states_packed, b.best_states_packed)
+    assert a.energy == b.energy and a.index == b.index
+
+
+# ---------------------------------------------------------------- energy + errors
+def test_energy_batch_matches_reference_formula(gpu):
+    rng = np.random.default_rng(0)
+    for n in (1, 31, 32, 33, 600, 1025):
+        q = gen.dense_uniform_qubo(n, seed=n)
+        states = rng.integers(0, 2, size=(67, n)).astype(np.uint8)
+        states[0] = 0
+        states[1] = 1
+        packed = pack_states(states)
+        with Problem.dense(q) as prob:
+            got = prob.energy_batch(packed)
+        want = np.array([ob.ref_energy(q, s.astype(np.int8)) for s in states])
+        np.testing.assert_allclose(got, want, rtol=REL, atol=1e-12)
+
+
+def test_error_paths(gpu):
+    q = gen.dense_uniform_qubo(8, seed=1)
+    bad = q.copy()
+    bad[0, 1] += 1.0
+    with pytest.raises(capi.OsaError) as ei:
+        Problem.dense(bad)
+    assert ei.value.code == capi.OSA_ERR_INVALID
+    with Problem.dense(q) as prob:
+        with pytest.raises(capi.OsaError):
+            prob.anneal(np.array([0.1, -1.0]), 2, 4)            # non-positive beta
+        with pytest.raises(capi.OsaError):
+            prob.anneal(geo(2), 2, 4, kernel_variant=capi.KID_SPARSE)
+        with pytest.raises(capi.OsaError):
+            prob.anneal(geo(2), 2, 4, kernel_variant=capi.KID_DENSE_SEQ)  # random mode

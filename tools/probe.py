@@ -1,0 +1,77 @@
+"""GPU probe: read-bandwidth ladder (L2 vs HBM) and quick throughput of the sweep kernels.
+Usage: python tools/probe.py [bw] [dense] [sparse]"""
+import json
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, ".")
+from onesolver_b200 import Problem, capi, device_name, measure_read_bandwidth  # noqa: E402
+from onesolver_b200 import problems as gen  # noqa: E402
+
+what = set(sys.argv[1:]) or {"bw", "dense", "sparse"}
+print("device:", device_name(0))
+
+if "bw" in what:
+    for mb in (8, 16, 32, 48, 64, 80, 96, 128, 256, 1024, 4096):
+        iters = max(2, min(200, 8192 // mb))
+        g = measure_read_bandwidth(mb << 20, iters)
+        print(json.dumps({"probe": "read_bw", "mb": mb, "iters": iters, "gbs": round(g, 1)}))
+
+
+def geo(n, lo, hi):
+    a = (hi / lo) ** (1.0 / max(1, n - 1))
+    return np.array([lo * a ** i for i in range(n)])
+
+
+def run_dense(n, prec, tries, sweeps, lo, hi, label):
+    q = gen.dense_uniform_qubo(n, seed=2024)
+    t0 = time.time()
+    with Problem.dense(q, sweep_precision=prec) as prob:
+        t1 = time.time()
+        sched = geo(sweeps, lo, hi)
+        for rep in range(2):
+            res = prob.anneal(sched, sweeps, tries, mode=capi.MODE_SEQUENTIAL_SWEEP)
+        st = res.stats
+    esz = st["q_elem_bytes"]
+    ld = -(-n // (1024 if esz == 4 else 512)) * (1024 if esz == 4 else 512)
+    sec = st["ms_sweep"] * 1e-3
+    out = {"probe": label, "n": n, "tries": tries, "sweeps": sweeps, "R": st["traj_per_batch"],
+           "grid": st["grid"], "ms_sweep": round(st["ms_sweep"], 3),
+           "ms_energy": round(st["ms_energy"], 3), "ms_total": round(st["ms_total"], 3),
+           "attempts_per_s": st["attempts"] / sec, "accept_frac": st["accepts"] / st["attempts"],
+           "row_fetches": st["row_fetches"], "init_rows": st["init_row_fetches"],
+           "row_gbs": (st["row_fetches"] + st["init_row_fetches"]) * ld * esz / sec / 1e9,
+           "unshared_gbs": st["accepts"] * ld * esz / sec / 1e9,
+           "upload_s": round(t1 - t0, 3), "energy": res.energy}
+    print(json.dumps(out))
+
+
+if "dense" in what:
+    s = np.sqrt(4096)
+    run_dense(4096, capi.SWEEP_F32, 148 * 8, 4, 0.3 * s, 0.02 * s, "dense4096_f32_1wave_hot2cold")
+    run_dense(4096, capi.SWEEP_F32, 148 * 8 * 4, 4, 0.3 * s, 0.02 * s, "dense4096_f32_4waves")
+    run_dense(4096, capi.SWEEP_F32, 148 * 8, 4, 0.01 * s, 0.002 * s, "dense4096_f32_cold")
+    run_dense(4096, capi.SWEEP_F32, 148 * 8, 4, 2 * s, 1 * s, "dense4096_f32_hot")
+    s = np.sqrt(1024)
+    run_dense(1024, capi.SWEEP_F64, 148 * 16, 8, 0.3 * s, 0.02 * s, "dense1024_f64")
+    run_dense(1024, capi.SWEEP_F32, 148 * 16, 8, 0.3 * s, 0.02 * s, "dense1024_f32")
+    run_dense(4096, capi.SWEEP_F64, 148 * 4, 2, 0.3 * 64, 0.02 * 64, "dense4096_f64")
+
+if "sparse" in what:
+    n = 5627
+    rowptr, col, val, diag = gen.sparse_random_graph(n, 15, seed=2028)
+    for prec, name in ((capi.SWEEP_F32, "f32"), (capi.SWEEP_F64, "f64")):
+        with Problem.csr(rowptr, col, val, diag, sweep_precision=prec) as prob:
+            sched = np.linspace(0.05, 2.0, 10)
+            for tries in (65536,):
+                res = prob.anneal(sched, 10, tries, mode=capi.MODE_SEQUENTIAL_SWEEP)
+                st = res.stats
+                sec = st["ms_sweep"] * 1e-3
+                print(json.dumps({"probe": "sparse5627_" + name, "tries": tries, "sweeps": 10,
+                                  "grid": st["grid"], "ms_sweep": round(st["ms_sweep"], 3),
+                                  "ms_energy": round(st["ms_energy"], 3),
+                                  "attempts_per_s": st["attempts"] / sec,
+                                  "accept_frac": st["accepts"] / st["attempts"],
+                                  "energy": res.energy}))
