@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py -- spin-flip attempts/s of the annealing hot path on B200 (BASELINE.json metric).
+
+Workload (N=1 and per GPU at N>1, weak scaling): BASELINE config 5's per-GPU share --
+synthetic dense random QUBO, N=4096, U(-1,1) coefficients, 131072 trajectories per GPU
+(1M tries / 8 GPUs), sequential-sweep mode, the reference's acceptance rule
+(annealing.hpp:106-108) on a geometric schedule built like one-solver-anneal.cpp:31-39.
+One "step" = one full osa_anneal call on that batch: initial fields + all sweeps + exact
+fp64 energies + argmin (+ the NCCL best-energy gather at N>1).
+
+  python bench.py --gpus N --steps K --warmup W            engine arm (this repo's CUDA path)
+  python bench.py --impl reference ...                     the reference's own algorithm
+                                                           (oracle restatement) on the host cores
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "spin-flip attempts/s, dense N=4096"
+UNIT = "attempts/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--n", type=int, default=4096)
+    ap.add_argument("--tries-per-gpu", type=int, default=131072)
+    ap.add_argument("--sweeps", type=int, default=8)
+    ap.add_argument("--beta-min", type=float, default=1.28)   # 0.02 * sqrt(N)
+    ap.add_argument("--beta-max", type=float, default=19.2)   # 0.30 * sqrt(N)
+    ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------- helpers
+def load_measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(smax)) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_instance(n):
+    from onesolver_b200 import problems as gen
+    return gen.dense_uniform_qubo(n, seed=2024 + 5)  # instance seed 2024 + config number
+
+
+def make_schedule(args):
+    from onesolver_b200 import construct_geometric_beta_schedule
+    if args.sweeps == 1:
+        return np.array([args.beta_min])
+    return construct_geometric_beta_schedule(args.beta_min, args.beta_max, args.sweeps)
+
+
+def config_dict(args, world):
+    return {"workload": f"BASELINE config 5 per-GPU share: dense N={args.n} U(-1,1) QUBO, "
+                        f"{args.tries_per_gpu} tries/GPU, {args.sweeps} sequential sweeps, "
+                        f"reference accept rule exp(-dE/beta)>u, geometric beta "
+                        f"{args.beta_min}->{args.beta_max}",
+            "n": args.n, "tries_per_gpu": args.tries_per_gpu, "sweeps": args.sweeps,
+            "mode": "sequential_sweep", "accept_rule": "reference", "schedule": "geometric",
+            "beta_min": args.beta_min, "beta_max": args.beta_max, "sweep_precision": args.precision,
+            "seed": 1234, "parallelism": f"trajectory shards x{world}, Q replicated",
+            "l2_hygiene": "Q copy streamed by the sweep is L2-resident by design (64 MiB fp32); "
+                          "each step also streams the 128 MiB fp64 copy (energy kernel) and writes "
+                          "64 MiB of states, which evicts it between steps"}
+
+
+# --------------------------------------------------------------------------- reference arm
+def cpu_reference_sample(args, q, seconds_target=12.0):
+    """Reference algorithm (full O(N^2) energy per attempt, annealing.hpp:85-126) restated in
+    oracle/osa_oracle.c, all host threads, bounded sample of the same instance."""
+    from oracle import binding as ob
+    cores = ob.num_threads()
+    n = q.shape[0]
+    flat = np.ascontiguousarray(q)
+    tries = cores * 2
+    # ~ n^2/2 MACs per attempt at ~1 GMAC/s/core
+    est_attempt_s = max(1e-7, n * n / 2 / 0.8e9)
+    iters = int(max(4, min(2000, seconds_target * cores / (tries * est_attempt_s))))
+    sched = np.geomspace(args.beta_min, args.beta_max, iters)
+    t0 = time.perf_counter()
+    ob.ref_anneal(flat, n, sched, iters, tries)
+    dt = time.perf_counter() - t0
+    attempts = tries * iters
+    return {"value": attempts / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{tries} tries x {iters} single-flip attempts (random-site, full energy "
+                      f"recompute) on the same N={n} instance, {dt:.2f} s wall; includes "
+                      f"{tries} initial energy evaluations"}, attempts, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    q = make_instance(args.n)
+    vals, times = [], []
+    base = None
+    for i in range(args.warmup + args.steps):
+        base, attempts, dt = cpu_reference_sample(args, q, seconds_target=4.0)
+        if i >= args.warmup:
+            vals.append(attempts)
+            times.append(dt)
+    value = sum(vals) / sum(times)
+    base["value"] = value
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": 1e3 * sum(times) / max(1, args.steps), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": config_dict(args, args.gpus), "cpu_baseline": base,
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
+                   "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+# --------------------------------------------------------------------------- engine arm
+def run_engine(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world == 1:
+        # convenience: relaunch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+               f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port",
+               "29533", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+
+    from onesolver_b200 import Problem, capi, measure_read_bandwidth, device_name
+
+    dist = None
+    torch = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    q = make_instance(args.n)
+    sched = make_schedule(args)
+    prec = capi.SWEEP_F32 if args.precision == "f32" else capi.SWEEP_F64
+    esz = 4 if args.precision == "f32" else 8
+    tries = args.tries_per_gpu
+    first_try = rank * tries
+    mode = capi.MODE_SEQUENTIAL_SWEEP
+
+    prob = Problem.dense(q, device=local_rank, sweep_precision=prec)  # inputs resident in HBM
+
+    def reduce_best(res):
+        """Best-energy/argmin gather: one NCCL collective of (energy, id, packed state)."""
+        if dist is None:
+            return res.energy, res.index
+        from onesolver_b200.multi import gather_best
+        e, idx, _ = gather_best(dist, torch, res.energy, res.index, res.state,
+                                torch.device("cuda", local_rank))
+        return e, idx
+
+    def step():
+        res = prob.anneal(sched, args.sweeps, tries, first_try=first_try, mode=mode)
+        e, idx = reduce_best(res)
+        return res.stats, e, idx
+
+    for _ in range(args.warmup):
+        step()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    sweep_ms = 0.0
+    energy_ms = 0.0
+    agg = {"attempts": 0, "accepts": 0, "row_fetches": 0, "init_row_fetches": 0, "launches": 0}
+    last = None
+    for _ in range(args.steps):
+        st, e, idx = step()
+        dev_ms += st["ms_total"]
+        sweep_ms += st["ms_sweep"]
+        energy_ms += st["ms_energy"]
+        for k in agg:
+            agg[k] += st[k]
+        last = (st, e, idx)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end-to-end through the C ABI with HOST buffers: upload Q, anneal, read results back
+    e2e_ms = None
+    if not args.no_e2e:
+        def e2e_step():
+            with Problem.dense(q, device=local_rank, sweep_precision=prec) as p2:
+                r = p2.anneal(sched, args.sweeps, tries, first_try=first_try, mode=mode,
+                              want_energies=True)
+                reduce_best(r)
+        e2e_step()  # warm-up (allocator, module load)
+        barrier()
+        t1 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        e2e_ms = (time.perf_counter() - t1) * 1e3
+
+    # ---- max over ranks
+    def rank_max(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    dev_ms = rank_max(dev_ms)
+    wall_ms = rank_max(wall_ms)
+    sweep_ms_max = rank_max(sweep_ms)
+    if e2e_ms is not None:
+        e2e_ms = rank_max(e2e_ms)
+
+    if rank == 0:
+        st = last[0]
+        attempts_per_step = st["attempts"] * world
+        # the collective (N>1) is outside the library's events: use the wall clock of the
+        # barrier-bracketed region as the step time when ranks > 1, device events at N=1
+        step_ms = (wall_ms if world > 1 else dev_ms) / args.steps
+        value = attempts_per_step / (step_ms * 1e-3)
+        ld = -(-args.n // (1024 if esz == 4 else 512)) * (1024 if esz == 4 else 512)
+        row_bytes = ld * esz
+        # dominant kernel: the sweep kernel (init fields + sweeps), one launch per step
+        alg_bytes_per_launch = (agg["row_fetches"] + agg["init_row_fetches"]) * row_bytes / args.steps
+        sweep_s_per_launch = sweep_ms / args.steps * 1e-3
+        achieved = alg_bytes_per_launch / sweep_s_per_launch / 1e9
+        l2_peak = measure_read_bandwidth(64 << 20, 64, device=local_rank)
+        peaks, peaks_src = load_measured_peaks()
+        q_bytes = args.n * ld * esz
+        bound = "l2" if q_bytes <= 100 * (1 << 20) else "hbm"
+        peak = l2_peak if bound == "l2" else peaks["hbm_gbs"]
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": config_dict(args, world),
+            "device": device_name(local_rank),
+            "breakdown_ms_per_step": {"sweep_kernel": sweep_ms / args.steps,
+                                      "exact_energy_kernel": energy_ms / args.steps,
+                                      "device_total": dev_ms / args.steps,
+                                      "wall": wall_ms / args.steps},
+            "accept_frac": agg["accepts"] / max(1, agg["attempts"]),
+            "traj_per_row_fetch": st["traj_per_batch"],
+            "sweep_only_attempts_per_s": attempts_per_step / (sweep_ms_max / args.steps * 1e-3),
+            "roofline": {
+                "bound": bound, "kernel": "k_dense_seq (init fields + sweeps)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": ("live osa_measure_read_bandwidth over a 64 MiB L2-resident buffer"
+                                if bound == "l2" else f"MEASURED_PEAKS.json hbm_gbs ({peaks_src})"),
+                "hbm_peak": peaks["hbm_gbs"], "hbm_peak_source": peaks_src,
+                "frac_of_hbm_peak": achieved / peaks["hbm_gbs"],
+                "algorithmic_bytes_per_launch": alg_bytes_per_launch,
+                "bytes_unshared_per_launch": agg["accepts"] * row_bytes / args.steps,
+                "traffic": None,
+            },
+            "clocks": clocks,
+            "gpu_launches": agg["launches"],
+            "best_energy": last[1], "best_index": last[2],
+        }
+        if e2e_ms is not None:
+            h2d = args.n * args.n * 8 + args.sweeps * 8
+            d2h = tries * 8 + ((args.n + 31) // 32) * 4 + 16 + 64
+            out["e2e"] = {"value": attempts_per_step / (e2e_ms / args.steps * 1e-3), "unit": UNIT,
+                          "ms_per_step": e2e_ms / args.steps,
+                          "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                          "what": "osa_problem_create_dense_f64(host Q) + osa_anneal(host outputs) "
+                                  "+ osa_problem_destroy per step, wall clock"}
+        if not args.no_cpu_baseline and world == 1:
+            base, _, _ = cpu_reference_sample(args, q)
+            out["cpu_baseline"] = base
+        print(json.dumps(out), flush=True)
+
+    prob.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == "__main__":
+    main()

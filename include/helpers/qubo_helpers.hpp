@@ -1,0 +1,83 @@
+// helpers/qubo_helpers.hpp -- turn a QUBOModel into the layouts the solvers consume.
+//
+// flatten_qubo keeps the reference's semantics
+// (/root/reference/include/helpers/qubo_helpers.hpp:26-44, layout pinned by
+// tests/qubo_helpers_test.cpp:14-29): a dense symmetric N x N vector, diagonal = linear
+// term (0 when absent), every stored coupling (a, b), a != b, added IN FULL to both
+// [a + bN] and [b + aN].  The reference performs N^2 hash lookups; this version walks
+// the stored terms once (O(N^2) zero fill + O(nnz)).
+// build_csr produces the symmetric CSR the sparse CUDA kernel takes
+// (osa_problem_create_csr_f64) without ever forming the dense matrix.
+#ifndef ONESOLVER_B200_HELPERS_QUBO_HELPERS_HPP_
+#define ONESOLVER_B200_HELPERS_QUBO_HELPERS_HPP_
+
+#include <algorithm>
+#include <cstddef>
+#include <cstdint>
+#include <map>
+#include <vector>
+
+#include "model/qubo.hpp"
+
+namespace helpers {
+
+template <class CoeffType>
+std::vector<CoeffType> flatten_qubo(const qubo::QUBOModel<int, CoeffType> &instance) {
+  const std::size_t n = instance.get_nodes();
+  std::vector<CoeffType> dense(n * n);
+  for (const auto &term : instance.linear_terms()) {
+    const auto i = static_cast<std::size_t>(term.first);
+    if (term.first >= 0 && i < n) dense[i + i * n] = term.second;
+  }
+  for (const auto &term : instance.quadratic_terms()) {
+    const int a = term.first.first, b = term.first.second;
+    if (a == b || a < 0 || b < 0) continue;  // the reference never looks up (i, i) couplings
+    const auto i = static_cast<std::size_t>(a), j = static_cast<std::size_t>(b);
+    if (i >= n || j >= n) continue;
+    dense[i + j * n] += term.second;
+    dense[j + i * n] += term.second;
+  }
+  return dense;
+}
+
+// Symmetric adjacency in CSR form: both directions stored, no diagonal entries,
+// columns ascending within a row, duplicate orientations (a,b)+(b,a) summed.
+template <class CoeffType>
+struct CsrQubo {
+  std::vector<std::int32_t> rowptr;
+  std::vector<std::int32_t> col;
+  std::vector<CoeffType> val;
+  std::vector<CoeffType> diag;
+};
+
+template <class CoeffType>
+CsrQubo<CoeffType> build_csr(const qubo::QUBOModel<int, CoeffType> &instance) {
+  const std::size_t n = instance.get_nodes();
+  CsrQubo<CoeffType> out;
+  out.diag.assign(n, CoeffType(0));
+  for (const auto &term : instance.linear_terms()) {
+    const auto i = static_cast<std::size_t>(term.first);
+    if (term.first >= 0 && i < n) out.diag[i] = term.second;
+  }
+  std::vector<std::map<std::int32_t, CoeffType>> rows(n);
+  for (const auto &term : instance.quadratic_terms()) {
+    const int a = term.first.first, b = term.first.second;
+    if (a == b || a < 0 || b < 0) continue;
+    if (static_cast<std::size_t>(a) >= n || static_cast<std::size_t>(b) >= n) continue;
+    rows[a][b] += term.second;
+    rows[b][a] += term.second;
+  }
+  out.rowptr.assign(n + 1, 0);
+  for (std::size_t i = 0; i < n; ++i) {
+    for (const auto &entry : rows[i]) {
+      out.col.push_back(entry.first);
+      out.val.push_back(entry.second);
+    }
+    out.rowptr[i + 1] = static_cast<std::int32_t>(out.col.size());
+  }
+  return out;
+}
+
+}  // namespace helpers
+
+#endif

@@ -1,0 +1,160 @@
+"""CPU tests of the C++ host layer (include/, app/): the ported reference unit tests, the CLIs,
+and the Boost-free `.qubo` reader fuzzed against the oracle's restatement of the Spirit grammar."""
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from oracle.qubo_format import QuboFormatError, load_qubo, parse_qubo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "build", "bin")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def host_binaries():
+    subprocess.run(["make", "-C", os.path.join(ROOT, "app"), "-s", "-j4"], check=True)
+
+
+def run(args, **kw):
+    return subprocess.run(args, capture_output=True, text=True, cwd=ROOT, **kw)
+
+
+def test_ported_reference_unit_tests():
+    r = run([os.path.join(BIN, "host_tests"), "examples"])
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 failed" in r.stdout
+
+
+def cpp_parse(tmp_path, text):
+    p = tmp_path / "case.qubo"
+    p.write_bytes(text.encode("latin-1"))
+    out = run([os.path.join(BIN, "host_tests"), "--dump-parse", str(p)]).stdout
+    lines = out.strip().splitlines()
+    if lines[0].startswith("REJECT"):
+        return None
+    n = int(lines[0].split()[1])
+    lin = {int(l.split()[1]): float(l.split()[2]) for l in lines[1:] if l.startswith("L")}
+    quad = {(int(l.split()[1]), int(l.split()[2])): float(l.split()[3]) for l in lines[1:]
+            if l.startswith("Q")}
+    return n, lin, quad
+
+
+def test_parser_matches_oracle_on_fuzzed_inputs(tmp_path):
+    rng = random.Random(7)
+    base = ("c qubo Target MaxNodes NumNodes NumLinks\np qubo 0 9 3 3\nc body\n0 0 -0.5\n0 1 2.0\n"
+            "1 1 3\n1 2 4\n2 2 -0.7e1\n2 8 .5\n")
+    mutations = [" ", "\t", "\n", "\r\n", "\r", "c", "p qubo", "1", "-", "+", ".", "e", "x", "0 ",
+                 "  ", "9 9 1\n", "inf", "nan", "\x01", "5.", "1e5", "c \x7f"]
+    cases = [base, base.rstrip("\n"), base + "  ", base + "\n", "", "\n", "c\n", "p qubo 0 1 1 0\n0 0 1"]
+    for _ in range(300):
+        t = base
+        for _ in range(rng.randint(1, 3)):
+            pos = rng.randrange(len(t) + 1)
+            if rng.random() < 0.5:
+                t = t[:pos] + rng.choice(mutations) + t[pos:]
+            else:
+                t = t[:pos] + t[pos + rng.randint(1, 4):]
+        cases.append(t)
+    accepted = 0
+    for text in cases:
+        try:
+            want = parse_qubo(text)
+        except QuboFormatError:
+            want = None
+        got = cpp_parse(tmp_path, text)
+        if want is None:
+            assert got is None, repr(text)
+        else:
+            accepted += 1
+            assert got is not None, repr(text)
+            assert got[0] == want[0] and got[1].keys() == want[1].keys() and got[2].keys() == want[2].keys(), repr(text)
+            for k, v in want[1].items():
+                assert got[1][k] == v or (np.isnan(v) and np.isnan(got[1][k])), repr(text)
+            for k, v in want[2].items():
+                assert got[2][k] == v or (np.isnan(v) and np.isnan(got[2][k])), repr(text)
+    assert accepted >= 20  # the fuzz must exercise the accept side too
+
+
+def test_cli_config1_host_defaults(tmp_path):
+    """BASELINE config 1: test1.qubo via one-solver-anneal --device-type host, defaults."""
+    out = tmp_path / "result.csv"
+    r = run([os.path.join(BIN, "one-solver-anneal"), "--input", "examples/test1.qubo", "--output",
+             str(out)])
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.splitlines()[:6] == [
+        "Reading input from: examples/test1.qubo", f"Output will be saved to: {out}",
+        "Schedule type: geometric", "Beta range: [0.1, 1]", "Number of iterations: 100",
+        "Number of tries: 100"]
+    assert out.read_text() == "0,1,2,3,energy\n1,1,0,1,-12\n"
+
+
+def test_cli_host_engine_equals_oracle_replay(tmp_path):
+    """The host device type runs the same engine as the GPU: its output must equal the oracle's
+    bit-exact replay on a Chimera instance shipped by the reference."""
+    inst = "tests/golden/chimera128/001.qubo"
+    out = tmp_path / "r.csv"
+    r = run([os.path.join(BIN, "one-solver-anneal"), "--input", inst, "--output", str(out),
+             "--num-iter", "400", "--num-tries", "24", "--schedule-type", "linear", "--beta-max",
+             "10", "--device-type", "cpu"])
+    assert r.returncode == 0, r.stderr
+    n, lin, quad = load_qubo(os.path.join(ROOT, inst))
+    q = ob.ref_flatten(n, lin, quad).reshape(n, n)
+    sched = ob.ref_schedule("linear", 0.1, 10.0, 400)
+    _, best, _, _ = ob.replay_dense(q, sched, 400, 24, mode=0)
+    e = ob.energy_packed(q, best)
+    k = int(np.argmin(e))
+    header, values = out.read_text().splitlines()
+    assert header == ",".join(str(i) for i in range(n)) + ",energy"
+    got = values.split(",")
+    want_state = [(int(best[k, i >> 5]) >> (i & 31)) & 1 for i in range(n)]
+    assert [int(v) for v in got[:n]] == want_state
+    assert abs(float(got[n]) - e[k]) <= 5e-6 * abs(e[k])
+
+
+@pytest.mark.parametrize("args,code,needle", [
+    (["--output", "x"], 255, "No input file provided."),
+    (["--input", "examples/test1.qubo"], 255, "No output file provided."),
+    (["--input", "a", "--output", "b", "--device-type", "tpu"], 255, "Unknown device type: tpu"),
+    (["--input", "a", "--output", "b", "--schedule-type", "cosine"], 255, "Unknown beta schedule: cosine"),
+    (["--input", "a", "--output", "b", "--beta-min", "-1"], 255, "both ends of beta range need to be positive"),
+    (["--input", "a", "--output", "b", "--beta-min", "2"], 255, "initial beta is not lesser than final beta"),
+    (["--input", "/nonexistent.qubo", "--output", "b"], 255, "can not open input file: /nonexistent.qubo"),
+    (["--input", "examples/dwave_doc.qubo", "--output", "/tmp/_x.csv"], 1, "error: Parsing failed. Incorrect file format."),
+    (["--bogus"], 1, "error: unrecognised option '--bogus'"),
+])
+def test_cli_error_paths(args, code, needle):
+    """Messages and exit codes of one-solver-anneal.cpp:78-115,129-136,171-173 (-1 == 255)."""
+    r = run([os.path.join(BIN, "one-solver-anneal")] + args)
+    assert r.returncode == code, (r.returncode, r.stderr)
+    assert needle in r.stderr
+
+
+def test_cli_help_and_exhaustive(tmp_path):
+    r = run([os.path.join(BIN, "one-solver-anneal"), "--help"])
+    assert r.returncode == 0 and r.stdout.startswith("Allowed options:")
+    for flag in ("--input", "--output", "--num-iter", "--num-tries", "--schedule-type", "--beta-min",
+                 "--beta-max", "--device-type"):
+        assert flag in r.stdout
+    out = tmp_path / "ex.csv"
+    r = run([os.path.join(BIN, "one-solver-exhaustive"), "--input", "examples/csp7.qubo", "--output",
+             str(out), "--device-type", "cpu"])
+    assert r.returncode == 0, r.stderr
+    assert out.read_text() == "0,1,2,3,4,5,6,energy\n1,1,1,0,0,1,0,-14\n"
+
+
+def test_gpu_device_type_fails_loudly_without_cuda(tmp_path):
+    """No CPU fallback: on a box without a CUDA device --device-type gpu must error out."""
+    from onesolver_b200 import capi
+    import ctypes
+    c = ctypes.c_int()
+    if capi.load().osa_device_count(ctypes.byref(c)) == 0 and c.value > 0:
+        pytest.skip("a CUDA device is present")
+    r = run([os.path.join(BIN, "one-solver-anneal"), "--input", "examples/test1.qubo", "--output",
+             str(tmp_path / "o.csv"), "--device-type", "gpu"])
+    assert r.returncode == 1
+    assert "No devices of given type could be initialized." in r.stderr
+    assert not (tmp_path / "o.csv").exists()
