@@ -85,6 +85,8 @@ typedef struct {
   int32_t grid;              /* CTAs launched by the sweep kernel */
   int32_t launches;          /* kernels launched by this call */
   int32_t reserved;
+  /* diagnostics of the dense sequential kernel: SM cycles summed over CTAs (0 elsewhere) */
+  uint64_t cyc_decide, cyc_apply, cyc_stage, cyc_init;
 } osa_stats;
 
 /* ---- library / device ---------------------------------------------------- */

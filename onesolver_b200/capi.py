@@ -55,6 +55,10 @@ class Stats(ctypes.Structure):
         ("grid", ctypes.c_int32),
         ("launches", ctypes.c_int32),
         ("reserved", ctypes.c_int32),
+        ("cyc_decide", ctypes.c_uint64),
+        ("cyc_apply", ctypes.c_uint64),
+        ("cyc_stage", ctypes.c_uint64),
+        ("cyc_init", ctypes.c_uint64),
     ]
 
     def as_dict(self):

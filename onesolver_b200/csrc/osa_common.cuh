@@ -127,6 +127,10 @@ struct Counters {  // device-side accumulators, one struct per call
   unsigned long long accepts;
   unsigned long long row_fetches;
   unsigned long long init_row_fetches;
+  unsigned long long cyc_decide;  // diagnostics: SM cycles (thread 0 of each CTA, summed) in P1
+  unsigned long long cyc_apply;   //              ... in P2 (row streaming)
+  unsigned long long cyc_stage;   //              ... staging tile/panel + barriers
+  unsigned long long cyc_init;    //              ... building the initial fields
   unsigned long long pad;
 };
 
@@ -135,6 +139,7 @@ struct DenseParams {
   const T *qoff;   // [n_rows_pad][ld], zero diagonal, symmetric, zero padded
   const T *diag;   // [ld], zero padded
   const T *tscale; // [num_iter]
+  cudaTextureObject_t qtex;  // qoff again as a 1D linear texture of 16-byte texels (second load path)
   size_t ld;
   int n;
   int num_iter;

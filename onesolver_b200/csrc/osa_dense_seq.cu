@@ -21,24 +21,39 @@
 //     keyed by (seed, trajectory, sweep, site).
 //   * best state: strict-improvement tracking (annealing.hpp:115-121) done lazily --
 //     the packed state is copied only when the walk LEAVES a best state.
+#include <cstdlib>
+
 #include "osa_common.cuh"
+#ifndef OSA_LDG_VARIANT
+#define OSA_LDG_VARIANT 0
+#endif
 
 namespace osa {
 
 namespace {
 
-constexpr int DS_THREADS = 256;
-constexpr int DS_WARPS = DS_THREADS / 32;
 
 template <typename VecT>
 __device__ __forceinline__ VecT ldg_stream(const VecT *p);
 template <>
 __device__ __forceinline__ float4 ldg_stream<float4>(const float4 *p) {
+#if OSA_LDG_VARIANT == 1
+  return __ldg(p);
+#elif OSA_LDG_VARIANT == 2
+  return __ldcs(p);
+#elif OSA_LDG_VARIANT == 3
+  float4 v;
+  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+#else
   float4 v;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                : "l"(p));
   return v;
+#endif
 }
 template <>
 __device__ __forceinline__ double2 ldg_stream<double2>(const double2 *p) {
@@ -49,93 +64,152 @@ __device__ __forceinline__ double2 ldg_stream<double2>(const double2 *p) {
   return v;
 }
 
-template <typename T, int CPT, int R>
+// second load path: the same 16 bytes through the texture unit (TLD), which ptxas tracks on a
+// different scoreboard than LDG
+template <typename VecT>
+__device__ __forceinline__ VecT tex_stream(cudaTextureObject_t t, int texel);
+template <>
+__device__ __forceinline__ float4 tex_stream<float4>(cudaTextureObject_t t, int texel) {
+  const uint4 u = tex1Dfetch<uint4>(t, texel);
+  return make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z),
+                     __uint_as_float(u.w));
+}
+template <>
+__device__ __forceinline__ double2 tex_stream<double2>(cudaTextureObject_t t, int texel) {
+  const uint4 u = tex1Dfetch<uint4>(t, texel);
+  return make_double2(__hiloint2double((int)u.y, (int)u.x), __hiloint2double((int)u.w, (int)u.z));
+}
+
+// TH threads per CTA; thread t owns NCH 16-byte column groups t, t+TH, ...
+template <typename T, int NCH, int R, int TH>
 struct Cfg {
   using VecT = typename Vec16<T>::type;
   static constexpr int V = Vec16<T>::V;
-  static constexpr int NCH = CPT / V;          // 16-byte column groups per thread
-  static constexpr int CHW = DS_THREADS * V;   // columns covered by one group across the CTA
-  static constexpr int MAXN = DS_THREADS * CPT;
-  static constexpr int NWP = MAXN / 32;        // state words (padded)
-  static constexpr int TPW = (R + DS_WARPS - 1) / DS_WARPS;  // trajectories decided per warp
+  static constexpr int WARPS = TH / 32;
+  static constexpr int CPT = NCH * V;      // columns per thread
+  static constexpr int CHW = TH * V;       // columns covered by one 16-byte group across the CTA
+  static constexpr int MAXN = TH * CPT;
+  static constexpr int NWP = MAXN / 32;    // state words (padded)
+  static constexpr int TPW = (R + WARPS - 1) / WARPS;  // trajectories decided per warp
 };
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
 
 // P2: stream the rows of block i0 whose site was accepted by at least one trajectory
 // and apply them.  am[r] bit s: trajectory r flipped site i0+s; sm[r] bit s: the spin
-// was 1 before the flip (sign -1).  Returns the union mask (rows fetched).
-template <typename T, int CPT, int R>
-__device__ __forceinline__ uint32_t apply_rows(const T *__restrict__ qoff, size_t ld, int i0,
-                                               const uint32_t (&am)[R], const uint32_t (&sm)[R],
-                                               T (&h)[R][CPT], int tid, int nch_act) {
-  using C = Cfg<T, CPT, R>;
+// was 1 before the flip (sign -1).
+//
+// Loads: a per-thread cp.async (LDGSTS) ring in shared memory, K rows deep.  Every thread
+// copies exactly the 16-byte pieces of a row that it will consume itself into its own ring
+// slots, so the ring needs no barrier of any kind: cp.async.wait_group gives in-order
+// completion, and the copies stay in flight while the thread runs the FMAs of earlier rows.
+// (Alternatives measured in profiles/r01/microbench_l2_streaming*.log: LDG into registers is
+// capped by the register file -- ptxas tracks all LDGs of a warp on one scoreboard, so loads
+// cannot overlap the warp's own arithmetic -- and a TMA ring pays a per-stage mbarrier
+// handshake; the cp.async ring streams at the full L2 rate including the read-back.)
+// Rows are applied strictly in site order.
+//
+// Arithmetic: per row the trajectories are handled in groups of G: a group is skipped with one
+// uniform branch when none of its members flipped the site, otherwise every member runs
+// h += m * q with m in {-1, 0, +1} (m = 0 leaves h unchanged).  Returns the union mask.
+template <typename T, int NCH, int R, int K, int TH, int G, int DBG = 0>
+__device__ __forceinline__ uint32_t apply_rows(const T *__restrict__ qoff, unsigned char *ring,
+                                               size_t ld, int i0, const uint32_t (&am)[R],
+                                               const uint32_t (&sm)[R],
+                                               T (&h)[R][NCH * Vec16<T>::V], int tid) {
+  using C = Cfg<T, NCH, R, TH>;
   using VecT = typename C::VecT;
-  constexpr int V = C::V, NCH = C::NCH, CHW = C::CHW;
+  constexpr int V = C::V, CHW = C::CHW;
+  constexpr int ROW_VECS = NCH * TH;  // 16-byte pieces per row
+  static_assert(R % G == 0, "R must be a multiple of the group size");
 
   uint32_t any = 0;
 #pragma unroll
   for (int r = 0; r < R; ++r) any |= am[r];
   if (any == 0) return 0;
 
+  uint32_t pos[R], neg[R], grp[R / G];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    pos[r] = am[r] & ~sm[r];
+    neg[r] = am[r] & sm[r];
+  }
+#pragma unroll
+  for (int g = 0; g < R / G; ++g) {
+    grp[g] = 0;
+#pragma unroll
+    for (int k = 0; k < G; ++k) grp[g] |= am[g * G + k];
+  }
+
   const T *base = qoff + (size_t)i0 * ld + (size_t)tid * V;
-  uint32_t rem = any;
-  auto next_row = [&]() -> int {
-    if (rem == 0) return -1;
-    const int s = __ffs(rem) - 1;
-    rem &= rem - 1;
-    return s;
+  VecT *mine = reinterpret_cast<VecT *>(ring) + tid;  // slot s, piece c: mine[s*ROW_VECS + c*TH]
+  const uint32_t mine_s = smem_addr(mine);
+  uint32_t rem_issue = any, rem_apply = any;
+  int slot_w = 0, slot_r = 0;
+
+  auto issue_next = [&]() {
+    if (rem_issue) {
+      const int s = __ffs(rem_issue) - 1;
+      rem_issue &= rem_issue - 1;
+      const T *rp = base + (size_t)s * ld;
+      const uint32_t dst = mine_s + (uint32_t)slot_w * (ROW_VECS * 16);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + c * (TH * 16)),
+                     "l"(rp + c * CHW)
+                     : "memory");
+      slot_w = (slot_w + 1 == K) ? 0 : slot_w + 1;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");  // one group per step, empty or not
   };
-  auto load_row = [&](VecT (&q)[NCH], int s) {
-    const T *rp = base + (size_t)s * ld;
+
+#pragma unroll 1
+  for (int k = 0; k < K - 1; ++k) issue_next();
+#pragma unroll 1
+  while (rem_apply) {
+    issue_next();
+    asm volatile("cp.async.wait_group %0;" ::"n"(K - 1) : "memory");
+    const int s = __ffs(rem_apply) - 1;
+    rem_apply &= rem_apply - 1;
+    const uint32_t bit = 1u << s;
+    T qv[NCH * V];
 #pragma unroll
-    for (int c = 0; c < NCH; ++c)
-      if (c < nch_act) q[c] = ldg_stream(reinterpret_cast<const VecT *>(rp + c * CHW));
-  };
-  auto apply_row = [&](const VecT (&q)[NCH], int s) {
+    for (int c = 0; c < NCH; ++c) vec_unpack<T>(mine[slot_r * ROW_VECS + c * TH], &qv[c * V]);
+    slot_r = (slot_r + 1 == K) ? 0 : slot_r + 1;
+    if (DBG == 1) {  // timing experiment: touch the data, skip the arithmetic
+      T acc = (T)0;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      if ((am[r] >> s) & 1u) {
-        const T sg = ((sm[r] >> s) & 1u) ? (T)-1 : (T)1;
+      for (int e = 0; e < NCH * V; ++e) acc += qv[e];
+      if (acc == (T)123456789) h[0][0] = acc;
+      continue;
+    }
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          if (c < nch_act) {
-            T qv[V];
-            vec_unpack<T>(q[c], qv);
+    for (int g = 0; g < R / G; ++g) {
+      if (grp[g] & bit) {
 #pragma unroll
-            for (int e = 0; e < V; ++e) h[r][c * V + e] = det::fma(sg, qv[e], h[r][c * V + e]);
-          }
+        for (int k = 0; k < G; ++k) {
+          const int r = g * G + k;
+          const T m = (pos[r] & bit) ? (T)1 : ((neg[r] & bit) ? (T)-1 : (T)0);
+#pragma unroll
+          for (int e = 0; e < NCH * V; ++e) h[r][e] = det::fma(m, qv[e], h[r][e]);
         }
       }
     }
-  };
-
-  // three rows in flight per thread, applied strictly in site order
-  VecT q0[NCH], q1[NCH], q2[NCH];
-  int s0 = next_row(), s1 = next_row(), s2 = next_row();
-  if (s0 >= 0) load_row(q0, s0);
-  if (s1 >= 0) load_row(q1, s1);
-  if (s2 >= 0) load_row(q2, s2);
-  for (;;) {
-    if (s0 < 0) break;
-    apply_row(q0, s0);
-    s0 = next_row();
-    if (s0 >= 0) load_row(q0, s0);
-    if (s1 < 0) break;
-    apply_row(q1, s1);
-    s1 = next_row();
-    if (s1 >= 0) load_row(q1, s1);
-    if (s2 < 0) break;
-    apply_row(q2, s2);
-    s2 = next_row();
-    if (s2 >= 0) load_row(q2, s2);
   }
   return any;
 }
 
-template <typename T, int CPT, int R>
-__global__ void __launch_bounds__(DS_THREADS, 1) k_dense_seq(const DenseParams<T> p) {
-  using C = Cfg<T, CPT, R>;
+template <typename T, int NCH, int R, int K, int TH, int G, int DBG = 0>
+__global__ void __launch_bounds__(TH, 1) k_dense_seq(const DenseParams<T> p) {
+  extern __shared__ __align__(128) unsigned char s_ring[];  // K rows, thread-private slots
+  using C = Cfg<T, NCH, R, TH>;
   using VecT = typename C::VecT;
-  constexpr int V = C::V, NCH = C::NCH, CHW = C::CHW, NWP = C::NWP, TPW = C::TPW;
+  constexpr int V = C::V, CPT = C::CPT, CHW = C::CHW, NWP = C::NWP, TPW = C::TPW;
+  constexpr int DS_WARPS = C::WARPS;
+  constexpr int TILE_VECS = 32 * 32 / V;  // 16-byte pieces of the diagonal tile
+  constexpr int TILE_PER_THREAD = (TILE_VECS + TH - 1) / TH;
 
   __shared__ __align__(16) T s_panel[R][32];
   __shared__ __align__(16) T s_tile[32][32];
@@ -147,22 +221,17 @@ __global__ void __launch_bounds__(DS_THREADS, 1) k_dense_seq(const DenseParams<T
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = p.n;
   const int nblk = (n + 31) >> 5;
-  const int nch_act = (int)(p.ld / CHW);  // host guarantees ld % CHW == 0 and ld <= MAXN
   const uint64_t batch0 = (uint64_t)blockIdx.x * R;
   const uint64_t left = p.num_tries - batch0;
   const int nvalid = left < (uint64_t)R ? (int)left : R;
 
-  // ---- local fields start at the diagonal (linear terms) ----
+  // ---- local fields start at the diagonal (linear terms); host guarantees ld == NCH*CHW ----
   T h[R][CPT];
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     T dv[V];
-#pragma unroll
-    for (int e = 0; e < V; ++e) dv[e] = (T)0;
-    if (c < nch_act) {
-      const VecT v = *reinterpret_cast<const VecT *>(p.diag + c * CHW + tid * V);
-      vec_unpack<T>(v, dv);
-    }
+    const VecT v = *reinterpret_cast<const VecT *>(p.diag + c * CHW + tid * V);
+    vec_unpack<T>(v, dv);
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
@@ -193,7 +262,36 @@ __global__ void __launch_bounds__(DS_THREADS, 1) k_dense_seq(const DenseParams<T
 
   unsigned long long cnt_rows = 0, cnt_init_rows = 0, cnt_acc = 0;
 
+  // the 32x32 diagonal tile of the NEXT block is fetched while the current block's rows
+  // stream, so its L2 latency never sits on the decision path
+  VecT tile_next[TILE_PER_THREAD];
+  auto fetch_tile = [&](int i0) {
+#pragma unroll
+    for (int t = 0; t < TILE_PER_THREAD; ++t) {
+      const int qi = tid + t * TH;
+      const int row = qi / (32 / V), cv = qi % (32 / V);
+      if (qi < TILE_VECS)
+        tile_next[t] = __ldg(reinterpret_cast<const VecT *>(p.qoff + (size_t)(i0 + row) * p.ld + i0 + cv * V));
+    }
+  };
+  auto store_tile = [&]() {
+#pragma unroll
+    for (int t = 0; t < TILE_PER_THREAD; ++t) {
+      const int qi = tid + t * TH;
+      const int row = qi / (32 / V), cv = qi % (32 / V);
+      if (qi < TILE_VECS) *reinterpret_cast<VecT *>(&s_tile[row][cv * V]) = tile_next[t];
+    }
+  };
+
+  long long t_decide = 0, t_apply = 0, t_stage = 0, t_init = 0, t_mark = clock64();
+  auto lap = [&](long long &acc) {
+    const long long now = clock64();
+    acc += now - t_mark;
+    t_mark = now;
+  };
+
   // ---- initial local fields: add the rows of the set spins, in site order ----
+  fetch_tile(0);
   for (int b = 0; b < nblk; ++b) {
     uint32_t am[R], sm[R];
 #pragma unroll
@@ -201,9 +299,11 @@ __global__ void __launch_bounds__(DS_THREADS, 1) k_dense_seq(const DenseParams<T
       am[r] = s_x[r][b];
       sm[r] = 0u;
     }
-    const uint32_t any = apply_rows<T, CPT, R>(p.qoff, p.ld, b * 32, am, sm, h, tid, nch_act);
+    const uint32_t any = apply_rows<T, NCH, R, K, TH, G, DBG>(p.qoff, s_ring, p.ld, b * 32, am, sm, h, tid);
     cnt_init_rows += (unsigned)__popc(any);
   }
+
+  lap(t_init);
 
   // ---- annealing ----
   double erel[TPW], best[TPW];
@@ -221,13 +321,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) k_dense_seq(const DenseParams<T
     for (int sw = 0; sw < p.sweeps_per_beta; ++sw, ++step) {
       for (int b = 0; b < nblk; ++b) {
         const int i0 = b * 32;
-        // -- stage the 32x32 diagonal tile and the 32-column panel of h --
-        for (int q = tid; q < 32 * 32 / V; q += DS_THREADS) {
-          const int row = q / (32 / V), cv = q % (32 / V);
-          const VecT v = *reinterpret_cast<const VecT *>(p.qoff + (size_t)(i0 + row) * p.ld + i0 +
-                                                         cv * V);
-          *reinterpret_cast<VecT *>(&s_tile[row][cv * V]) = v;
-        }
+        // -- stage the (prefetched) diagonal tile and the 32-column panel of h --
+        store_tile();
         {
           const int cb = i0 / CHW;
           const int rel = tid * V - (i0 % CHW);
@@ -244,6 +339,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) k_dense_seq(const DenseParams<T
           }
         }
         __syncthreads();
+        lap(t_stage);
 
         // -- P1: sequential decisions, one warp per trajectory --
 #pragma unroll
@@ -296,16 +392,22 @@ __global__ void __launch_bounds__(DS_THREADS, 1) k_dense_seq(const DenseParams<T
           }
         }
         __syncthreads();
+        lap(t_decide);
 
         // -- P2: stream accepted rows, update all local fields --
+        {
+          const int bn = (b + 1 == nblk) ? 0 : b + 1;  // next block (wraps into the next sweep)
+          fetch_tile(bn * 32);
+        }
         uint32_t am[R], sm[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           am[r] = s_acc[r];
           sm[r] = s_sign[r];
         }
-        const uint32_t any = apply_rows<T, CPT, R>(p.qoff, p.ld, i0, am, sm, h, tid, nch_act);
+        const uint32_t any = apply_rows<T, NCH, R, K, TH, G, DBG>(p.qoff, s_ring, p.ld, i0, am, sm, h, tid);
         cnt_rows += (unsigned)__popc(any);
+        lap(t_apply);
       }
     }
   }
@@ -329,51 +431,90 @@ __global__ void __launch_bounds__(DS_THREADS, 1) k_dense_seq(const DenseParams<T
   if (tid == 0) {
     atomicAdd(&p.counters->row_fetches, cnt_rows);
     atomicAdd(&p.counters->init_row_fetches, cnt_init_rows);
+    atomicAdd(&p.counters->cyc_decide, (unsigned long long)t_decide);
+    atomicAdd(&p.counters->cyc_apply, (unsigned long long)t_apply);
+    atomicAdd(&p.counters->cyc_stage, (unsigned long long)t_stage);
+    atomicAdd(&p.counters->cyc_init, (unsigned long long)t_init);
   }
 }
 
-template <typename T, int CPT, int R>
+template <typename T, int NCH, int R, int K, int TH, int G, int DBG = 0>
 cudaError_t launch_cfg(const DenseParams<T> &p, cudaStream_t s, LaunchInfo *info) {
   const uint64_t grid64 = (p.num_tries + R - 1) / R;
   if (grid64 == 0 || grid64 > 0x7fffffffull) return cudaErrorInvalidValue;
-  k_dense_seq<T, CPT, R><<<(unsigned)grid64, DS_THREADS, 0, s>>>(p);
+  const size_t smem = (size_t)K * NCH * TH * 16;  // the cp.async ring
+  auto kern = k_dense_seq<T, NCH, R, K, TH, G, DBG>;
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  kern<<<(unsigned)grid64, TH, smem, s>>>(p);
   if (info) {
     info->grid = (int)grid64;
-    info->block = DS_THREADS;
+    info->block = TH;
     info->traj_per_batch = R;
-    info->smem = 0;
+    info->smem = smem;
   }
   return cudaGetLastError();
 }
 
 }  // namespace
 
-// column capacity per config: 256 threads * CPT
+// column capacity: 256 threads * NCH 16-byte groups, NCH <= 8
 bool dense_seq_supported(int n, int elem_bytes) {
   if (n < 1) return false;
   return elem_bytes == 4 ? n <= 8192 : n <= 4096;
 }
 
-// ld contract: multiple of CHW (1024 floats / 512 doubles) and <= MAXN of the chosen config
+// ld contract: ld is a multiple of 1024 floats / 512 doubles (one 16-byte group per thread of a
+// 256-thread CTA).  Per shape: R trajectories per CTA (h = R*NCH*16 bytes of registers per thread)
+// and a ring of K rows (K*NCH*4 KiB of shared memory, <= 192 KiB).
 template <>
 cudaError_t launch_dense_seq<float>(const DenseParams<float> &p, cudaStream_t s, LaunchInfo *info) {
   if (p.ld % 1024 != 0) return cudaErrorInvalidValue;
-  if (p.ld <= 1024) return launch_cfg<float, 4, 16>(p, s, info);
-  if (p.ld <= 2048) return launch_cfg<float, 8, 16>(p, s, info);
-  if (p.ld <= 4096) return launch_cfg<float, 16, 8>(p, s, info);
-  if (p.ld <= 8192) return launch_cfg<float, 32, 4>(p, s, info);
-  return cudaErrorInvalidValue;
+  switch (p.ld / 1024) {
+    case 1: return launch_cfg<float, 1, 16, 16, 256, 4>(p, s, info);
+    case 2: return launch_cfg<float, 2, 16, 16, 256, 4>(p, s, info);
+    case 3: return launch_cfg<float, 3, 12, 12, 256, 4>(p, s, info);
+    case 4: {
+      const char *e = getenv("OSA_DS_CFG");  // tuning knob (tools/probe.py): R*1000 + K*10 + G
+      const int cfg = e ? atoi(e) : 8121;
+      switch (cfg) {
+        case 8081: return launch_cfg<float, 4, 8, 8, 256, 1>(p, s, info);
+        case 8122: return launch_cfg<float, 4, 8, 12, 256, 2>(p, s, info);
+        case 8124: return launch_cfg<float, 4, 8, 12, 256, 4>(p, s, info);
+        case 8128: return launch_cfg<float, 4, 8, 12, 256, 8>(p, s, info);
+        case 10121: return launch_cfg<float, 4, 10, 12, 256, 1>(p, s, info);
+        case 10122: return launch_cfg<float, 4, 10, 12, 256, 2>(p, s, info);
+        case 12121: return launch_cfg<float, 4, 12, 12, 256, 1>(p, s, info);
+        case 12122: return launch_cfg<float, 4, 12, 12, 256, 2>(p, s, info);
+        case 12124: return launch_cfg<float, 4, 12, 12, 256, 4>(p, s, info);
+        case 81211: return launch_cfg<float, 4, 8, 12, 256, 1, 1>(p, s, info);  // loads only
+        case 81212: return launch_cfg<float, 4, 8, 12, 256, 1, 2>(p, s, info);  // (unused)
+        default: return launch_cfg<float, 4, 8, 12, 256, 1>(p, s, info);
+      }
+    }
+    case 5: return launch_cfg<float, 5, 8, 9, 256, 2>(p, s, info);
+    case 6: return launch_cfg<float, 6, 8, 8, 256, 2>(p, s, info);
+    case 7: return launch_cfg<float, 7, 6, 6, 256, 2>(p, s, info);
+    case 8: return launch_cfg<float, 8, 6, 6, 256, 2>(p, s, info);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 template <>
 cudaError_t launch_dense_seq<double>(const DenseParams<double> &p, cudaStream_t s,
                                      LaunchInfo *info) {
   if (p.ld % 512 != 0) return cudaErrorInvalidValue;
-  if (p.ld <= 512) return launch_cfg<double, 2, 16>(p, s, info);
-  if (p.ld <= 1024) return launch_cfg<double, 4, 16>(p, s, info);
-  if (p.ld <= 2048) return launch_cfg<double, 8, 8>(p, s, info);
-  if (p.ld <= 4096) return launch_cfg<double, 16, 4>(p, s, info);
-  return cudaErrorInvalidValue;
+  switch (p.ld / 512) {
+    case 1: return launch_cfg<double, 1, 16, 16, 256, 4>(p, s, info);
+    case 2: return launch_cfg<double, 2, 16, 16, 256, 4>(p, s, info);
+    case 3: return launch_cfg<double, 3, 12, 12, 256, 4>(p, s, info);
+    case 4: return launch_cfg<double, 4, 8, 12, 256, 2>(p, s, info);
+    case 5: return launch_cfg<double, 5, 6, 9, 256, 2>(p, s, info);
+    case 6: return launch_cfg<double, 6, 6, 8, 256, 2>(p, s, info);
+    case 7: return launch_cfg<double, 7, 4, 6, 256, 2>(p, s, info);
+    case 8: return launch_cfg<double, 8, 4, 6, 256, 2>(p, s, info);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 }  // namespace osa

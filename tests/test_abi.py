@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(capi.AnnealParams) == 48
-    assert ctypes.sizeof(capi.Stats) == 72
+    assert ctypes.sizeof(capi.Stats) == 104
 
 
 def test_no_cpu_fallback_without_a_device():

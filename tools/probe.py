@@ -44,7 +44,9 @@ def run_dense(n, prec, tries, sweeps, lo, hi, label):
            "row_fetches": st["row_fetches"], "init_rows": st["init_row_fetches"],
            "row_gbs": (st["row_fetches"] + st["init_row_fetches"]) * ld * esz / sec / 1e9,
            "unshared_gbs": st["accepts"] * ld * esz / sec / 1e9,
-           "upload_s": round(t1 - t0, 3), "energy": res.energy}
+           "upload_s": round(t1 - t0, 3), "energy": res.energy,
+           "kcyc_per_cta": {k: round(st[k] / max(1, st["grid"]) / 1e3, 1)
+                            for k in ("cyc_init", "cyc_stage", "cyc_decide", "cyc_apply")}}
     print(json.dumps(out))
 
 
@@ -58,6 +60,15 @@ if "dense" in what:
     run_dense(1024, capi.SWEEP_F64, 148 * 16, 8, 0.3 * s, 0.02 * s, "dense1024_f64")
     run_dense(1024, capi.SWEEP_F32, 148 * 16, 8, 0.3 * s, 0.02 * s, "dense1024_f32")
     run_dense(4096, capi.SWEEP_F64, 148 * 4, 2, 0.3 * 64, 0.02 * 64, "dense4096_f64")
+
+if "cfg" in what:
+    import os
+    s = np.sqrt(4096)
+    for cfg in os.environ.get("OSA_PROBE_CFGS", "821,822,824,731,631,632,541,441,451,452,411").split(","):
+        os.environ["OSA_DS_CFG"] = cfg
+        r = 8 if cfg.startswith("8") else int(cfg[:2])
+        run_dense(4096, capi.SWEEP_F32, 148 * r, 4, 0.3 * s, 0.02 * s, "cfg%s_hot2cold" % cfg)
+    os.environ.pop("OSA_DS_CFG")
 
 if "sparse" in what:
     n = 5627
