@@ -58,7 +58,6 @@ struct osa_problem {
   size_t rows_pad = 0;    // rows allocated (multiple of 32)
   void *d_qoff = nullptr; // zero-diagonal symmetric copy, sweep precision
   void *d_diag = nullptr; // [ld] sweep precision
-  cudaTextureObject_t qtex = 0;  // d_qoff as a 1D linear texture of 16-byte texels
   size_t ld64 = 0;
   double *d_q64 = nullptr; // [n][ld64] original values incl. diagonal (exact energies)
   // csr
@@ -220,21 +219,6 @@ int create_dense(const TIn *qsym, int n, int device, int prec, osa_problem **out
   if (bad) {
     fail(OSA_ERR_INVALID, "Q is not symmetric (expected helpers::flatten_qubo layout)");
     return bail(OSA_ERR_INVALID);
-  }
-  {
-    // second, independently tracked load path for the sweep kernel (see osa_dense_seq.cu)
-    cudaResourceDesc rd = {};
-    rd.resType = cudaResourceTypeLinear;
-    rd.res.linear.devPtr = p->d_qoff;
-    rd.res.linear.desc = cudaCreateChannelDesc<uint4>();
-    rd.res.linear.sizeInBytes = p->rows_pad * p->ld * esz;
-    cudaTextureDesc td = {};
-    td.readMode = cudaReadModeElementType;
-    cudaError_t te = cudaCreateTextureObject(&p->qtex, &rd, &td, nullptr);
-    if (te != cudaSuccess) {
-      p->qtex = 0;  // the kernel falls back to its single-path variant
-      cudaGetLastError();
-    }
   }
   *out = p;
   return OSA_OK;
@@ -431,7 +415,6 @@ int osa_problem_destroy(osa_problem *p) {
     cudaFree(p->d_val64);
     cudaFree(p->d_diag64);
   } else {
-    if (p->qtex) cudaDestroyTextureObject(p->qtex);
     cudaFree(p->d_qoff);
     cudaFree(p->d_diag);
     cudaFree(p->d_q64);
@@ -555,7 +538,6 @@ int osa_anneal(osa_problem *p, const double *beta_schedule, const osa_anneal_par
       using T = decltype(tag);
       DenseParams<T> dp;
       dp.qoff = (const T *)p->d_qoff;
-      dp.qtex = p->qtex;
       dp.diag = (const T *)p->d_diag;
       dp.tscale = (const T *)p->d_tscale;
       dp.ld = p->ld;

@@ -139,7 +139,6 @@ struct DenseParams {
   const T *qoff;   // [n_rows_pad][ld], zero diagonal, symmetric, zero padded
   const T *diag;   // [ld], zero padded
   const T *tscale; // [num_iter]
-  cudaTextureObject_t qtex;  // qoff again as a 1D linear texture of 16-byte texels (second load path)
   size_t ld;
   int n;
   int num_iter;

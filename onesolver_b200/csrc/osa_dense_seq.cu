@@ -7,6 +7,8 @@
 //   * local fields h[r][:] live in REGISTERS, column-sliced over the 256 threads
 //     (thread t owns 16-byte column groups t, t+256, ...), so a Q row is fetched
 //     from L2 once per CTA and applied to every trajectory that flipped that site;
+//     rows travel through a per-thread cp.async ring in shared memory (see apply_rows)
+//     and fp32 fields are updated with the packed fma.rn.f32x2 of sm_100;
 //   * sites are processed in blocks of 32 (one bit-packed spin word):
 //       P1 "decide": one warp per trajectory walks the block sequentially on a
 //          32-value copy of h (one lane per site) and the 32x32 diagonal tile of Q,
@@ -24,61 +26,53 @@
 #include <cstdlib>
 
 #include "osa_common.cuh"
-#ifndef OSA_LDG_VARIANT
-#define OSA_LDG_VARIANT 0
-#endif
 
 namespace osa {
 
 namespace {
 
 
-template <typename VecT>
-__device__ __forceinline__ VecT ldg_stream(const VecT *p);
-template <>
-__device__ __forceinline__ float4 ldg_stream<float4>(const float4 *p) {
-#if OSA_LDG_VARIANT == 1
-  return __ldg(p);
-#elif OSA_LDG_VARIANT == 2
-  return __ldcs(p);
-#elif OSA_LDG_VARIANT == 3
-  float4 v;
-  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(p));
-  return v;
-#else
-  float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(p));
-  return v;
-#endif
-}
-template <>
-__device__ __forceinline__ double2 ldg_stream<double2>(const double2 *p) {
-  double2 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
-               : "=d"(v.x), "=d"(v.y)
-               : "l"(p));
-  return v;
-}
+// Local-field storage of one trajectory in one thread: N values.  For fp32 the values are kept as
+// 64-bit register pairs so that the row update can use the packed FMA of sm_100
+// (fma.rn.f32x2: two IEEE fp32 FMAs per instruction, bit-identical to two scalar fma.rn).
+template <typename T, int N>
+struct Field;
 
-// second load path: the same 16 bytes through the texture unit (TLD), which ptxas tracks on a
-// different scoreboard than LDG
-template <typename VecT>
-__device__ __forceinline__ VecT tex_stream(cudaTextureObject_t t, int texel);
-template <>
-__device__ __forceinline__ float4 tex_stream<float4>(cudaTextureObject_t t, int texel) {
-  const uint4 u = tex1Dfetch<uint4>(t, texel);
-  return make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z),
-                     __uint_as_float(u.w));
-}
-template <>
-__device__ __forceinline__ double2 tex_stream<double2>(cudaTextureObject_t t, int texel) {
-  const uint4 u = tex1Dfetch<uint4>(t, texel);
-  return make_double2(__hiloint2double((int)u.y, (int)u.x), __hiloint2double((int)u.w, (int)u.z));
-}
+template <int N>
+struct Field<double, N> {
+  double v[N];
+  __device__ __forceinline__ double get(int i) const { return v[i]; }
+  __device__ __forceinline__ void set(int i, double x) { v[i] = x; }
+  // v[i] += m * q[i]
+  __device__ __forceinline__ void axpy(double m, const double (&q)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = det::fma(m, q[i], v[i]);
+  }
+};
+
+template <int N>
+struct Field<float, N> {
+  static_assert(N % 2 == 0, "fp32 fields are stored as pairs");
+  unsigned long long p[N / 2];
+  __device__ __forceinline__ float get(int i) const {
+    return __uint_as_float((i & 1) ? (uint32_t)(p[i >> 1] >> 32) : (uint32_t)p[i >> 1]);
+  }
+  __device__ __forceinline__ void set(int i, float x) {
+    const unsigned long long b = __float_as_uint(x);
+    p[i >> 1] = (i & 1) ? ((p[i >> 1] & 0xffffffffull) | (b << 32))
+                        : ((p[i >> 1] & 0xffffffff00000000ull) | b);
+  }
+  __device__ __forceinline__ void axpy(float m, const float (&q)[N]) {
+    const unsigned long long mb = __float_as_uint(m);
+    const unsigned long long mm = (mb << 32) | mb;
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+      const unsigned long long qq =
+          ((unsigned long long)__float_as_uint(q[2 * i + 1]) << 32) | __float_as_uint(q[2 * i]);
+      asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(p[i]) : "l"(qq), "l"(mm));
+    }
+  }
+};
 
 // TH threads per CTA; thread t owns NCH 16-byte column groups t, t+TH, ...
 template <typename T, int NCH, int R, int TH>
@@ -118,7 +112,7 @@ template <typename T, int NCH, int R, int K, int TH, int G, int DBG = 0>
 __device__ __forceinline__ uint32_t apply_rows(const T *__restrict__ qoff, unsigned char *ring,
                                                size_t ld, int i0, const uint32_t (&am)[R],
                                                const uint32_t (&sm)[R],
-                                               T (&h)[R][NCH * Vec16<T>::V], int tid) {
+                                               Field<T, NCH * Vec16<T>::V> (&h)[R], int tid) {
   using C = Cfg<T, NCH, R, TH>;
   using VecT = typename C::VecT;
   constexpr int V = C::V, CHW = C::CHW;
@@ -182,7 +176,7 @@ __device__ __forceinline__ uint32_t apply_rows(const T *__restrict__ qoff, unsig
       T acc = (T)0;
 #pragma unroll
       for (int e = 0; e < NCH * V; ++e) acc += qv[e];
-      if (acc == (T)123456789) h[0][0] = acc;
+      if (acc == (T)123456789) h[0].set(0, acc);
       continue;
     }
 #pragma unroll
@@ -192,8 +186,7 @@ __device__ __forceinline__ uint32_t apply_rows(const T *__restrict__ qoff, unsig
         for (int k = 0; k < G; ++k) {
           const int r = g * G + k;
           const T m = (pos[r] & bit) ? (T)1 : ((neg[r] & bit) ? (T)-1 : (T)0);
-#pragma unroll
-          for (int e = 0; e < NCH * V; ++e) h[r][e] = det::fma(m, qv[e], h[r][e]);
+          h[r].axpy(m, qv);
         }
       }
     }
@@ -226,7 +219,7 @@ __global__ void __launch_bounds__(TH, 1) k_dense_seq(const DenseParams<T> p) {
   const int nvalid = left < (uint64_t)R ? (int)left : R;
 
   // ---- local fields start at the diagonal (linear terms); host guarantees ld == NCH*CHW ----
-  T h[R][CPT];
+  Field<T, CPT> h[R];
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     T dv[V];
@@ -235,7 +228,7 @@ __global__ void __launch_bounds__(TH, 1) k_dense_seq(const DenseParams<T> p) {
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
-      for (int e = 0; e < V; ++e) h[r][c * V + e] = dv[e];
+      for (int e = 0; e < V; ++e) h[r].set(c * V + e, dv[e]);
   }
 
   // ---- initial spins (replaces random.bit(), annealing.hpp:90-92) ----
@@ -333,7 +326,7 @@ __global__ void __launch_bounds__(TH, 1) k_dense_seq(const DenseParams<T> p) {
 #pragma unroll
                 for (int r = 0; r < R; ++r)
 #pragma unroll
-                  for (int e = 0; e < V; ++e) s_panel[r][rel + e] = h[r][c * V + e];
+                  for (int e = 0; e < V; ++e) s_panel[r][rel + e] = h[r].get(c * V + e);
               }
             }
           }
@@ -475,20 +468,14 @@ cudaError_t launch_dense_seq<float>(const DenseParams<float> &p, cudaStream_t s,
     case 2: return launch_cfg<float, 2, 16, 16, 256, 4>(p, s, info);
     case 3: return launch_cfg<float, 3, 12, 12, 256, 4>(p, s, info);
     case 4: {
-      const char *e = getenv("OSA_DS_CFG");  // tuning knob (tools/probe.py): R*1000 + K*10 + G
-      const int cfg = e ? atoi(e) : 8121;
-      switch (cfg) {
+      // tuning knob used by tools/probe.py (R*1000 + K*10 + G); the default is the measured best
+      const char *e = getenv("OSA_DS_CFG");
+      switch (e ? atoi(e) : 0) {
         case 8081: return launch_cfg<float, 4, 8, 8, 256, 1>(p, s, info);
         case 8122: return launch_cfg<float, 4, 8, 12, 256, 2>(p, s, info);
-        case 8124: return launch_cfg<float, 4, 8, 12, 256, 4>(p, s, info);
         case 8128: return launch_cfg<float, 4, 8, 12, 256, 8>(p, s, info);
-        case 10121: return launch_cfg<float, 4, 10, 12, 256, 1>(p, s, info);
-        case 10122: return launch_cfg<float, 4, 10, 12, 256, 2>(p, s, info);
-        case 12121: return launch_cfg<float, 4, 12, 12, 256, 1>(p, s, info);
         case 12122: return launch_cfg<float, 4, 12, 12, 256, 2>(p, s, info);
-        case 12124: return launch_cfg<float, 4, 12, 12, 256, 4>(p, s, info);
-        case 81211: return launch_cfg<float, 4, 8, 12, 256, 1, 1>(p, s, info);  // loads only
-        case 81212: return launch_cfg<float, 4, 8, 12, 256, 1, 2>(p, s, info);  // (unused)
+        case 81211: return launch_cfg<float, 4, 8, 12, 256, 1, 1>(p, s, info);  // loads only (timing)
         default: return launch_cfg<float, 4, 8, 12, 256, 1>(p, s, info);
       }
     }

@@ -4,7 +4,7 @@ TAG=${1:-iter}; PROF=${2:-0}
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q -x -p no:cacheprovider --tb=short --timeout=240 2>&1 | tail -15 > gpurun_out/pytest_$TAG.log
 tail -3 gpurun_out/pytest_$TAG.log
-OSA_PROBE_CFGS=8121,81211,8081,8122,8124,8128,10121,10122,12121,12122,12124 timeout 600 python tools/probe.py dense cfg > gpurun_out/probe_$TAG.log 2>&1; cat gpurun_out/probe_$TAG.log
+timeout 600 python tools/probe.py dense sparse > gpurun_out/probe_$TAG.log 2>&1; cat gpurun_out/probe_$TAG.log
 if [ "$PROF" = "1" ]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_dense_seq -c 1 \
     -o gpurun_out/prof_dense_seq_$TAG python bench.py --steps 1 --warmup 0 --tries-per-gpu 1184 --sweeps 2 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full_$TAG.log 2>&1

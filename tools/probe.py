@@ -66,7 +66,7 @@ if "cfg" in what:
     s = np.sqrt(4096)
     for cfg in os.environ.get("OSA_PROBE_CFGS", "821,822,824,731,631,632,541,441,451,452,411").split(","):
         os.environ["OSA_DS_CFG"] = cfg
-        r = 8 if cfg.startswith("8") else int(cfg[:2])
+        r = 8 if cfg[0] in "85" else int(cfg[:2])
         run_dense(4096, capi.SWEEP_F32, 148 * r, 4, 0.3 * s, 0.02 * s, "cfg%s_hot2cold" % cfg)
     os.environ.pop("OSA_DS_CFG")
 
