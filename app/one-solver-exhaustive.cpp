@@ -48,9 +48,15 @@ int main(int argc, char *argv[]) {
     }
     auto instance = qubo::QUBOModel<int, double>::load(qubo_file);
 
-    // the enumeration itself runs on the host threads for every device type (see exhaustive.hpp);
-    // "gpu" is accepted for flag compatibility and maps to all host cores
-    devices::queue q(*devices::construct_device_selector(device_type == "gpu" ? "cpu" : device_type));
+    std::unique_ptr<devices::queue> q_ptr;
+    try {
+      q_ptr.reset(new devices::queue(*devices::construct_device_selector(device_type)));
+    } catch (const std::runtime_error &e) {
+      std::cerr << "No devices of given type could be initialized." << std::endl;
+      std::cerr << "error: " << e.what() << "\n";
+      return 1;
+    }
+    devices::queue &q = *q_ptr;
     std::cout << "Using device: " << q.device_name() << std::endl;
 
     auto solution = exhaustive::solve(q, instance);

@@ -141,7 +141,8 @@ def cpu_reference_sample(args, q, seconds_target=12.0):
     """Reference algorithm (full O(N^2) energy per attempt, annealing.hpp:85-126) restated in
     oracle/osa_oracle.c, all host threads, bounded sample of the same instance."""
     from oracle import binding as ob
-    cores = ob.num_threads()
+    # all host cores, regardless of OMP_NUM_THREADS (torchrun sets it to 1)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
     n = q.shape[0]
     flat = np.ascontiguousarray(q)
     tries = cores * 2
@@ -150,7 +151,7 @@ def cpu_reference_sample(args, q, seconds_target=12.0):
     iters = int(max(4, min(2000, seconds_target * cores / (tries * est_attempt_s))))
     sched = np.geomspace(args.beta_min, args.beta_max, iters)
     t0 = time.perf_counter()
-    ob.ref_anneal(flat, n, sched, iters, tries)
+    ob.ref_anneal(flat, n, sched, iters, tries, num_threads=cores)
     dt = time.perf_counter() - t0
     attempts = tries * iters
     return {"value": attempts / dt, "unit": UNIT, "cores": cores, "kind": "port",

@@ -6,19 +6,22 @@
 // strict minimum of each range (:104-137) and takes the first minimum over ranges (:158-166), so
 // the winner is the LOWEST state integer attaining the minimum; state bit i is variable i
 // (helpers/ulong_to_vec.hpp).  Per-state energies use the reference's summation order (upper
-// triangle, i then j), so ties resolve identically.  This implementation runs on the host threads
-// for every device type (it is the N <= 30-ish oracle named by BASELINE.json, not the hot path)
-// and lifts the reference's `1 << n_bits` int limit to 40 bits.
+// triangle, i then j), so ties resolve identically.  A "gpu" queue runs the CUDA search
+// (osa_exhaustive_dense_f64, Gray-code incremental energies, onesolver_b200/csrc/osa_exhaustive.cu);
+// "cpu"/"host" queues enumerate on the host threads.  Both lift the reference's `1 << n_bits` int
+// limit (exhaustive.hpp:67) to 40 bits.
 #ifndef ONESOLVER_B200_EXHAUSTIVE_HPP_
 #define ONESOLVER_B200_EXHAUSTIVE_HPP_
 
 #include <algorithm>
 #include <limits>
 #include <stdexcept>
+#include <string>
 #include <thread>
 #include <vector>
 
 #include "helpers/devices.hpp"
+#include "helpers/qubo_helpers.hpp"
 #include "helpers/ulong_to_vec.hpp"
 #include "model/qubo.hpp"
 #include "model/solution.hpp"
@@ -30,6 +33,27 @@ qubo::Solution solve(devices::queue &q, qubo::QUBOModel<NodeType, CoefType> &qub
   const unsigned n_bits = static_cast<unsigned>(qubos.get_nodes());
   if (n_bits == 0) throw std::invalid_argument("exhaustive: the model has no variables");
   if (n_bits > 40) throw std::invalid_argument("exhaustive: at most 40 variables are supported");
+
+  if (q.is_gpu()) {
+    qubo::QUBOModel<int, double> as_double;
+    as_double.set_nodes(static_cast<int>(n_bits));
+    for (unsigned i = 0; i < n_bits; ++i) {
+      as_double.add_variable(static_cast<int>(i), qubos.get_variable(static_cast<NodeType>(i)));
+      for (unsigned j = i + 1; j < n_bits; ++j) {
+        const double c = qubos.get_connection(
+            std::make_pair(static_cast<NodeType>(i), static_cast<NodeType>(j)));
+        if (c != 0.0) as_double.add_connection(std::make_pair(static_cast<int>(i), static_cast<int>(j)), c);
+      }
+    }
+    const auto flat = helpers::flatten_qubo(as_double);
+    std::vector<unsigned char> state(n_bits);
+    double energy = 0.0;
+    if (osa_exhaustive_dense_f64(flat.data(), static_cast<int>(n_bits), q.cuda_device(),
+                                 state.data(), &energy) != OSA_OK) {
+      throw std::runtime_error(std::string("osa_exhaustive_dense_f64: ") + osa_last_error());
+    }
+    return qubo::Solution(state.begin(), state.end(), energy);
+  }
 
   // upper-triangular coefficient table, as in the reference (:44-61)
   std::vector<double> upper(static_cast<std::size_t>(n_bits) * n_bits, 0.0);

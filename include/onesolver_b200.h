@@ -128,6 +128,12 @@ int osa_anneal(osa_problem *p, const double *beta_schedule, const osa_anneal_par
 /* sa::energy (annealing.hpp:31-40) for a batch of packed states, fp64 on the device */
 int osa_energy_batch(osa_problem *p, const uint32_t *states_packed, uint64_t count, double *out);
 
+/* ---- brute-force ground state for n <= 40: CUDA counterpart of exhaustive::solve
+ *      (include/exhaustive/exhaustive.hpp:29-167).  qsym in flatten_qubo layout; the winner is the
+ *      LOWEST state integer among the minima (bit i = variable i), energy by the reference formula. */
+int osa_exhaustive_dense_f64(const double *qsym, int n, int device, uint8_t *best_state,
+                             double *best_energy);
+
 /* ---- measurement helper: achieved read bandwidth of a `bytes`-sized buffer swept
  *      `iters` times by all SMs (L2-resident if it fits, HBM otherwise); GB/s.      */
 int osa_measure_read_bandwidth(int device, size_t bytes, int iters, double *gbs);

@@ -11,6 +11,7 @@ from .anneal import (  # noqa: F401
     construct_linear_beta_schedule,
     device_count,
     device_name,
+    exhaustive,
     measure_read_bandwidth,
     pack_states,
     unpack_states,

@@ -131,6 +131,17 @@ class Problem:
         return out
 
 
+def exhaustive(qsym, device=0):
+    """exhaustive::solve on the GPU: (state uint8[N], energy) of the lowest-index ground state."""
+    q = np.ascontiguousarray(qsym, dtype=np.float64)
+    n = q.shape[0]
+    state = np.empty(n, dtype=np.uint8)
+    e = ctypes.c_double()
+    capi.check(capi.load().osa_exhaustive_dense_f64(q.ctypes.data, n, device, state.ctypes.data,
+                                                    ctypes.byref(e)))
+    return state, e.value
+
+
 def device_count():
     c = ctypes.c_int()
     capi.check(capi.load().osa_device_count(ctypes.byref(c)))

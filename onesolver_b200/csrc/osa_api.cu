@@ -17,6 +17,11 @@
 
 using namespace osa;
 
+namespace osa {
+cudaError_t exhaustive_search(const double *qsym_host, int n, unsigned long long *x_best,
+                              double *e_best, std::string *msg);
+}
+
 // ---------------------------------------------------------------------------
 // error plumbing
 // ---------------------------------------------------------------------------
@@ -635,6 +640,26 @@ int osa_energy_batch(osa_problem *p, const uint32_t *states_packed, uint64_t cou
   CUDA_TRY(cudaMemcpyAsync(out, p->d_energy, count * sizeof(double), cudaMemcpyDeviceToHost,
                            p->stream));
   CUDA_TRY(cudaStreamSynchronize(p->stream));
+  return OSA_OK;
+}
+
+int osa_exhaustive_dense_f64(const double *qsym, int n, int device, uint8_t *best_state,
+                             double *best_energy) {
+  if (!qsym || !best_state || !best_energy) return fail(OSA_ERR_INVALID, "null argument");
+  if (n < 1 || n > 40) return fail(OSA_ERR_UNSUPPORTED, "exhaustive search supports 1 <= n <= 40");
+  for (int i = 0; i < n; ++i)
+    for (int j = i + 1; j < n; ++j)
+      if (!(qsym[(size_t)i * n + j] == qsym[(size_t)j * n + i]))
+        return fail(OSA_ERR_INVALID, "Q is not symmetric (expected helpers::flatten_qubo layout)");
+  int rc = select_device(device);
+  if (rc) return rc;
+  unsigned long long x = 0;
+  double e = 0.0;
+  std::string msg;
+  cudaError_t err = exhaustive_search(qsym, n, &x, &e, &msg);
+  if (err != cudaSuccess) return fail(OSA_ERR_CUDA, "%s", msg.c_str());
+  for (int i = 0; i < n; ++i) best_state[i] = (uint8_t)((x >> i) & 1ull);
+  *best_energy = e;
   return OSA_OK;
 }
 

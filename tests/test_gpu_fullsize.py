@@ -1,0 +1,109 @@
+"""GPU tests at BASELINE.json's full shapes (configs 3, 4, 5): too large for a full oracle run, so
+they check size-independent properties plus an oracle replay of a sample of the trajectories.
+
+Properties: returned (state, energy) self-consistent under the reference energy function, winner =
+first minimum of the per-trajectory energies, prefix stability in num_tries, shard
+invariance, counters consistent, and sampled trajectories bit-exact vs the host replay."""
+import numpy as np
+import pytest
+
+from onesolver_b200 import Problem, capi, unpack_states
+from onesolver_b200 import problems as gen
+from oracle import binding as ob
+
+pytestmark = pytest.mark.gpu
+REL = 1e-9
+
+
+def check_common(res, tries):
+    e = res.best_energies
+    k = int(np.argmin(e))
+    assert res.index == k and res.energy == e[k]
+    assert res.stats["attempts"] > 0 and 0 < res.stats["accepts"] < res.stats["attempts"]
+    assert res.stats["row_fetches"] <= res.stats["accepts"]
+    assert e.shape == (tries,) and np.isfinite(e).all()
+
+
+def test_config3_dense_fp64_n1024_16384_tries(gpu):
+    """BASELINE config 3 shape: dense fp64 N=1024, 16384 tries (12 sweeps here; the sweep count
+    only scales run time)."""
+    n, tries, sweeps = 1024, 16384, 12
+    q = gen.dense_uniform_qubo(n, seed=2024 + 3)
+    sched = ob.ref_schedule("geometric", 0.6, 10.0, sweeps)
+    with Problem.dense(q, sweep_precision=capi.SWEEP_F64) as prob:
+        res = prob.anneal(sched, sweeps, tries, mode=capi.MODE_SEQUENTIAL_SWEEP,
+                          want_energies=True, want_states=True)
+        small = prob.anneal(sched, sweeps, 300, mode=capi.MODE_SEQUENTIAL_SWEEP,
+                            want_energies=True, want_states=True)
+        tail = prob.anneal(sched, sweeps, 100, first_try=tries - 100,
+                           mode=capi.MODE_SEQUENTIAL_SWEEP, want_states=True)
+    check_common(res, tries)
+    assert res.stats["kernel_id"] == capi.KID_DENSE_SEQ and res.stats["q_elem_bytes"] == 8
+    # prefix stability and shard invariance
+    np.testing.assert_array_equal(small.best_states_packed, res.best_states_packed[:300])
+    np.testing.assert_array_equal(small.best_energies, res.best_energies[:300])
+    np.testing.assert_array_equal(tail.best_states_packed, res.best_states_packed[-100:])
+    # sampled trajectories vs the oracle: replay ids 0..23 and 16360..16383
+    for first in (0, tries - 24):
+        _, best, _, _ = ob.replay_dense(q, sched, sweeps, 24, mode=1, first_try=first,
+                                        dtype=np.float64)
+        np.testing.assert_array_equal(res.best_states_packed[first:first + 24], best)
+        e_ref = ob.energy_packed(q, best)
+        np.testing.assert_allclose(res.best_energies[first:first + 24], e_ref, rtol=REL)
+    # the winner under the reference energy function
+    e_win = ob.ref_energy(q, res.state.astype(np.int8))
+    assert abs(e_win - res.energy) <= REL * abs(e_win)
+
+
+def test_config5_dense_n4096_131072_tries_per_gpu(gpu):
+    """BASELINE config 5 per-GPU share: dense N=4096, 131072 tries (1 sweep here)."""
+    n, tries = 4096, 131072
+    q = gen.dense_uniform_qubo(n, seed=2024 + 5)
+    sched = np.array([8.0])
+    with Problem.dense(q, sweep_precision=capi.SWEEP_F32) as prob:
+        res = prob.anneal(sched, 1, tries, mode=capi.MODE_SEQUENTIAL_SWEEP, want_energies=True,
+                          want_states=True)
+        shard = prob.anneal(sched, 1, 64, first_try=70000, mode=capi.MODE_SEQUENTIAL_SWEEP,
+                            want_energies=True, want_states=True)
+    check_common(res, tries)
+    assert res.stats["traj_per_batch"] >= 8 and res.stats["q_elem_bytes"] == 4
+    assert res.stats["attempts"] == tries * n
+    np.testing.assert_array_equal(shard.best_states_packed, res.best_states_packed[70000:70064])
+    np.testing.assert_array_equal(shard.best_energies, res.best_energies[70000:70064])
+    r = res.stats["traj_per_batch"]
+    first = 131072 - 2 * r
+    _, best, _, cnt = ob.replay_dense(q, sched, 1, 2 * r, mode=1, first_try=first, dtype=np.float32,
+                                      batch_r=r)
+    np.testing.assert_array_equal(res.best_states_packed[first:], best)
+    e_ref = ob.energy_packed(q, best)
+    np.testing.assert_allclose(res.best_energies[first:], e_ref, rtol=REL)
+    e_win = ob.ref_energy(q, res.state.astype(np.int8))
+    assert abs(e_win - res.energy) <= REL * abs(e_win)
+    assert (unpack_states(res.best_states_packed[res.index], n)[0] == res.state).all()
+
+
+def test_config4_sparse_n5627_65536_tries_linear_schedule(gpu):
+    """BASELINE config 4 shape: sparse degree<=15 QUBO on N=5627 (CSR), 65536 tries, linear schedule."""
+    n, tries, sweeps = 5627, 65536, 3
+    rowptr, col, val, diag = gen.sparse_random_graph(n, 15, seed=2024 + 4)
+    sched = ob.ref_schedule("linear", 0.05, 1.0, sweeps)
+    with Problem.csr(rowptr, col, val, diag, sweep_precision=capi.SWEEP_F32) as prob:
+        res = prob.anneal(sched, sweeps, tries, mode=capi.MODE_SEQUENTIAL_SWEEP,
+                          want_energies=True, want_states=True)
+        shard = prob.anneal(sched, sweeps, 96, first_try=4000, mode=capi.MODE_SEQUENTIAL_SWEEP,
+                            want_states=True)
+    e = res.best_energies
+    k = int(np.argmin(e))
+    assert res.index == k and res.energy == e[k]
+    assert res.stats["kernel_id"] == capi.KID_SPARSE
+    np.testing.assert_array_equal(shard.best_states_packed, res.best_states_packed[4000:4096])
+    for first in (0, tries - 40):
+        _, best, _, _ = ob.replay_csr(rowptr, col, val, diag, sched, sweeps, 40, mode=1,
+                                      first_try=first, dtype=np.float32)
+        np.testing.assert_array_equal(res.best_states_packed[first:first + 40], best)
+        # reference energy function on the sparse instance: diag.x + sum_{i<j} q_ij x_i x_j
+        x = unpack_states(best, n).astype(np.float64)
+        rows = np.repeat(np.arange(n), np.diff(rowptr))
+        upper = col > rows
+        e_ref = x @ diag + ((x[:, rows[upper]] * x[:, col[upper]]) @ val[upper])
+        np.testing.assert_allclose(res.best_energies[first:first + 40], e_ref, rtol=REL, atol=1e-9)

@@ -216,3 +216,65 @@ def test_error_paths(gpu):
             prob.anneal(geo(2), 2, 4, kernel_variant=capi.KID_SPARSE)
         with pytest.raises(capi.OsaError):
             prob.anneal(geo(2), 2, 4, kernel_variant=capi.KID_DENSE_SEQ)  # random mode
+
+
+# ---------------------------------------------------------------- exhaustive search (next row 1)
+def test_cuda_exhaustive_matches_reference_restatement(gpu):
+    """osa_exhaustive_dense_f64 vs the oracle's restatement of exhaustive.hpp: same ground energy,
+    same (lowest-index) ground state, on the reference's test instances and random ones."""
+    import json
+    import os
+    from onesolver_b200 import exhaustive
+    from oracle.qubo_format import parse_qubo
+    here = os.path.dirname(os.path.abspath(__file__))
+    g = json.load(open(os.path.join(here, "golden", "reference_vectors.json")))
+    for case in g["exhaustive_test"]:
+        n, lin, quad = parse_qubo(case["qubo"])
+        q = ob.ref_flatten(n, lin, quad).reshape(n, n)
+        state, e = exhaustive(q)
+        want_state, want_e = ob.ref_exhaustive(q, n, 7)
+        assert abs(e - case["energy"]) < 1e-13 and e == want_e
+        np.testing.assert_array_equal(state, want_state)
+    for n, seed, integer in [(1, 0, True), (2, 1, False), (17, 2, True), (19, 3, False),
+                             (22, 4, True), (24, 2026, True), (25, 5, False)]:
+        q = gen.dense_integer_qubo(n, seed) if integer else gen.dense_uniform_qubo(n, seed)
+        state, e = exhaustive(q)
+        want_state, want_e = ob.ref_exhaustive(q, n, 8)
+        assert e == want_e, (n, e, want_e)
+        np.testing.assert_array_equal(state, want_state)
+    # degenerate instance: all states of the zero matrix tie -> lowest state integer (all zeros)
+    state, e = exhaustive(np.zeros((12, 12)))
+    assert e == 0.0 and not state.any()
+
+
+def test_cli_gpu_paths(gpu, tmp_path):
+    """one-solver-anneal / one-solver-exhaustive with --device-type gpu (BASELINE config 1 on GPU)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-C", os.path.join(root, "app"), "-s", "-j4"], check=True)
+    out = tmp_path / "a.csv"
+    r = subprocess.run([os.path.join(root, "build/bin/one-solver-anneal"), "--input",
+                        "examples/test1.qubo", "--output", str(out), "--device-type", "gpu"],
+                       capture_output=True, text=True, cwd=root)
+    assert r.returncode == 0, r.stderr
+    assert "Using device: NVIDIA" in r.stdout
+    assert out.read_text() == "0,1,2,3,energy\n1,1,0,1,-12\n"
+    # host and gpu device types run the same engine: identical output on a Chimera instance
+    args = ["--input", "tests/golden/chimera128/001.qubo", "--num-iter", "300", "--num-tries", "40",
+            "--schedule-type", "linear", "--beta-max", "10"]
+    outs = {}
+    for dev in ("gpu", "cpu"):
+        o = tmp_path / f"{dev}.csv"
+        r = subprocess.run([os.path.join(root, "build/bin/one-solver-anneal")] + args +
+                           ["--output", str(o), "--device-type", dev], capture_output=True,
+                           text=True, cwd=root)
+        assert r.returncode == 0, r.stderr
+        outs[dev] = o.read_text()
+    assert outs["gpu"] == outs["cpu"]
+    ex = tmp_path / "e.csv"
+    r = subprocess.run([os.path.join(root, "build/bin/one-solver-exhaustive"), "--input",
+                        "examples/csp13.qubo", "--output", str(ex), "--device-type", "gpu"],
+                       capture_output=True, text=True, cwd=root)
+    assert r.returncode == 0, r.stderr
+    assert ex.read_text() == "0,1,2,3,4,5,6,7,8,9,10,11,12,energy\n1,1,1,0,1,1,0,0,0,0,0,0,0,-32\n"
