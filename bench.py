@@ -39,7 +39,7 @@ def parse_args():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--n", type=int, default=4096)
     ap.add_argument("--tries-per-gpu", type=int, default=131072)
-    ap.add_argument("--sweeps", type=int, default=8)
+    ap.add_argument("--sweeps", type=int, default=32)
     ap.add_argument("--beta-min", type=float, default=1.28)   # 0.02 * sqrt(N)
     ap.add_argument("--beta-max", type=float, default=19.2)   # 0.30 * sqrt(N)
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
@@ -123,7 +123,7 @@ def make_schedule(args):
 
 
 def config_dict(args, world):
-    return {"workload": f"BASELINE config 5 per-GPU share: dense N={args.n} U(-1,1) QUBO, "
+    return {"workload": f"BASELINE config 5 per-GPU share (1M tries / 8 GPUs): dense N={args.n} U(-1,1) QUBO, "
                         f"{args.tries_per_gpu} tries/GPU, {args.sweeps} sequential sweeps, "
                         f"reference accept rule exp(-dE/beta)>u, geometric beta "
                         f"{args.beta_min}->{args.beta_max}",
@@ -264,8 +264,11 @@ def run_engine(args):
     # ---- end-to-end through the C ABI with HOST buffers: upload Q, anneal, read results back
     e2e_ms = None
     if not args.no_e2e:
+        from onesolver_b200 import pinned_copy
+        q_pinned, free_pinned = pinned_copy(q)  # the step's input lives in pinned host memory
+
         def e2e_step():
-            with Problem.dense(q, device=local_rank, sweep_precision=prec) as p2:
+            with Problem.dense(q_pinned, device=local_rank, sweep_precision=prec) as p2:
                 r = p2.anneal(sched, args.sweeps, tries, first_try=first_try, mode=mode,
                               want_energies=True)
                 reduce_best(r)
@@ -276,6 +279,7 @@ def run_engine(args):
             e2e_step()
         barrier()
         e2e_ms = (time.perf_counter() - t1) * 1e3
+        free_pinned()
 
     # ---- max over ranks
     def rank_max(x):
@@ -333,6 +337,10 @@ def run_engine(args):
                 "algorithmic_bytes_per_launch": alg_bytes_per_launch,
                 "bytes_unshared_per_launch": agg["accepts"] * row_bytes / args.steps,
                 "traffic": None,
+                "traffic_note": "ncu --set full on a one-wave launch of the same kernel "
+                                "(profiles/r01/ncu_k_dense_seq_v7_summary.txt): L2 sectors read "
+                                "26.8 GB = the algorithmic row bytes of that launch, DRAM read "
+                                "133 MB (Q enters L2 once)",
             },
             "clocks": clocks,
             "gpu_launches": agg["launches"],

@@ -128,6 +128,11 @@ int osa_anneal(osa_problem *p, const double *beta_schedule, const osa_anneal_par
 /* sa::energy (annealing.hpp:31-40) for a batch of packed states, fp64 on the device */
 int osa_energy_batch(osa_problem *p, const uint32_t *states_packed, uint64_t count, double *out);
 
+/* ---- optional pinned host staging buffers (cudaMallocHost / cudaFreeHost) for callers that
+ *      upload large Q matrices repeatedly; any host pointer is accepted by the calls above. */
+int osa_host_alloc_pinned(size_t bytes, void **out);
+int osa_host_free_pinned(void *ptr);
+
 /* ---- brute-force ground state for n <= 40: CUDA counterpart of exhaustive::solve
  *      (include/exhaustive/exhaustive.hpp:29-167).  qsym in flatten_qubo layout; the winner is the
  *      LOWEST state integer among the minima (bit i = variable i), energy by the reference formula. */

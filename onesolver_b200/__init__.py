@@ -14,5 +14,6 @@ from .anneal import (  # noqa: F401
     exhaustive,
     measure_read_bandwidth,
     pack_states,
+    pinned_copy,
     unpack_states,
 )

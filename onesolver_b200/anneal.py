@@ -131,6 +131,17 @@ class Problem:
         return out
 
 
+def pinned_copy(array):
+    """Copy `array` into page-locked host memory (osa_host_alloc_pinned); returns (ndarray, free)."""
+    a = np.ascontiguousarray(array)
+    ptr = ctypes.c_void_p()
+    capi.check(capi.load().osa_host_alloc_pinned(a.nbytes, ctypes.byref(ptr)))
+    buf = (ctypes.c_byte * a.nbytes).from_address(ptr.value)
+    out = np.frombuffer(buf, dtype=a.dtype).reshape(a.shape)
+    out[...] = a
+    return out, (lambda: capi.load().osa_host_free_pinned(ptr))
+
+
 def exhaustive(qsym, device=0):
     """exhaustive::solve on the GPU: (state uint8[N], energy) of the lowest-index ground state."""
     q = np.ascontiguousarray(qsym, dtype=np.float64)

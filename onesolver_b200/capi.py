@@ -21,7 +21,8 @@ EXPORTED_SYMBOLS = [
     "osa_abi_version", "osa_last_error", "osa_device_count", "osa_device_name",
     "osa_kernel_name", "osa_problem_create_dense_f64", "osa_problem_create_dense_f32",
     "osa_problem_create_csr_f64", "osa_problem_destroy", "osa_problem_size", "osa_anneal",
-    "osa_energy_batch", "osa_exhaustive_dense_f64", "osa_measure_read_bandwidth",
+    "osa_energy_batch", "osa_exhaustive_dense_f64", "osa_host_alloc_pinned",
+    "osa_host_free_pinned", "osa_measure_read_bandwidth",
 ]
 
 
@@ -99,6 +100,8 @@ def load():
     lib.osa_anneal.argtypes = [vp, vp, P(AnnealParams), vp, vp, vp, P(ctypes.c_double), P(u64),
                                P(Stats)]
     lib.osa_energy_batch.argtypes = [vp, vp, u64, vp]
+    lib.osa_host_alloc_pinned.argtypes = [sz, P(vp)]
+    lib.osa_host_free_pinned.argtypes = [vp]
     lib.osa_exhaustive_dense_f64.argtypes = [vp, i32, i32, vp, P(ctypes.c_double)]
     lib.osa_measure_read_bandwidth.argtypes = [i32, sz, i32, P(ctypes.c_double)]
     _lib = lib

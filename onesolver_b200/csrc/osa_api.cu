@@ -643,6 +643,22 @@ int osa_energy_batch(osa_problem *p, const uint32_t *states_packed, uint64_t cou
   return OSA_OK;
 }
 
+int osa_host_alloc_pinned(size_t bytes, void **out) {
+  if (!out || bytes == 0) return fail(OSA_ERR_INVALID, "bad argument");
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+    return fail(OSA_ERR_NO_DEVICE, "no CUDA device available");
+  CUDA_TRY(cudaMallocHost(out, bytes));
+  return OSA_OK;
+}
+
+int osa_host_free_pinned(void *ptr) {
+  if (!ptr) return OSA_OK;
+  CUDA_TRY(cudaFreeHost(ptr));
+  return OSA_OK;
+}
+
 int osa_exhaustive_dense_f64(const double *qsym, int n, int device, uint8_t *best_state,
                              double *best_energy) {
   if (!qsym || !best_state || !best_energy) return fail(OSA_ERR_INVALID, "null argument");

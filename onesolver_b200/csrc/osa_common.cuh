@@ -188,6 +188,8 @@ struct LaunchInfo { int grid; int block; int traj_per_batch; size_t smem; };
 template <typename T>
 cudaError_t launch_dense_seq(const DenseParams<T> &p, cudaStream_t s, LaunchInfo *info);
 template <typename T>
+cudaError_t launch_dense_seq_ws(const DenseParams<T> &p, cudaStream_t s, LaunchInfo *info);
+template <typename T>
 cudaError_t launch_dense_generic(const DenseParams<T> &p, cudaStream_t s, LaunchInfo *info);
 template <typename T>
 cudaError_t launch_sparse(const SparseParams<T> &p, cudaStream_t s, LaunchInfo *info);

@@ -1,0 +1,174 @@
+// osa_dense_seq.cuh -- pieces shared by the dense sequential-sweep kernels
+// (osa_dense_seq.cu: single-role CTA; osa_dense_seq_ws.cu: warp-specialised decide/apply overlap).
+#pragma once
+
+#include "osa_common.cuh"
+
+namespace osa {
+namespace dseq {
+
+// Local-field storage of one trajectory in one thread: N values.  For fp32 the values are kept as
+// 64-bit register pairs so that the row update can use the packed FMA of sm_100
+// (fma.rn.f32x2: two IEEE fp32 FMAs per instruction, bit-identical to two scalar fma.rn).
+template <typename T, int N>
+struct Field;
+
+template <int N>
+struct Field<double, N> {
+  double v[N];
+  __device__ __forceinline__ double get(int i) const { return v[i]; }
+  __device__ __forceinline__ void set(int i, double x) { v[i] = x; }
+  // v[i] += m * q[i]
+  __device__ __forceinline__ void axpy(double m, const double (&q)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = det::fma(m, q[i], v[i]);
+  }
+};
+
+template <int N>
+struct Field<float, N> {
+  static_assert(N % 2 == 0, "fp32 fields are stored as pairs");
+  unsigned long long p[N / 2];
+  __device__ __forceinline__ float get(int i) const {
+    return __uint_as_float((i & 1) ? (uint32_t)(p[i >> 1] >> 32) : (uint32_t)p[i >> 1]);
+  }
+  __device__ __forceinline__ void set(int i, float x) {
+    const unsigned long long b = __float_as_uint(x);
+    p[i >> 1] = (i & 1) ? ((p[i >> 1] & 0xffffffffull) | (b << 32))
+                        : ((p[i >> 1] & 0xffffffff00000000ull) | b);
+  }
+  __device__ __forceinline__ void axpy(float m, const float (&q)[N]) {
+    const unsigned long long mb = __float_as_uint(m);
+    const unsigned long long mm = (mb << 32) | mb;
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+      const unsigned long long qq =
+          ((unsigned long long)__float_as_uint(q[2 * i + 1]) << 32) | __float_as_uint(q[2 * i]);
+      asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(p[i]) : "l"(qq), "l"(mm));
+    }
+  }
+};
+
+// TH threads per CTA; thread t owns NCH 16-byte column groups t, t+TH, ...
+template <typename T, int NCH, int R, int TH>
+struct Cfg {
+  using VecT = typename Vec16<T>::type;
+  static constexpr int V = Vec16<T>::V;
+  static constexpr int WARPS = TH / 32;
+  static constexpr int CPT = NCH * V;      // columns per thread
+  static constexpr int CHW = TH * V;       // columns covered by one 16-byte group across the CTA
+  static constexpr int MAXN = TH * CPT;
+  static constexpr int NWP = MAXN / 32;    // state words (padded)
+  static constexpr int TPW = (R + WARPS - 1) / WARPS;  // trajectories decided per warp
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// P2: stream the rows of block i0 whose site was accepted by at least one trajectory
+// and apply them.  am[r] bit s: trajectory r flipped site i0+s; sm[r] bit s: the spin
+// was 1 before the flip (sign -1).
+//
+// Loads: a per-thread cp.async (LDGSTS) ring in shared memory, K rows deep.  Every thread
+// copies exactly the 16-byte pieces of a row that it will consume itself into its own ring
+// slots, so the ring needs no barrier of any kind: cp.async.wait_group gives in-order
+// completion, and the copies stay in flight while the thread runs the FMAs of earlier rows.
+// (Alternatives measured in profiles/r01/microbench_l2_streaming*.log: LDG into registers is
+// capped by the register file -- ptxas tracks all LDGs of a warp on one scoreboard, so loads
+// cannot overlap the warp's own arithmetic -- and a TMA ring pays a per-stage mbarrier
+// handshake; the cp.async ring streams at the full L2 rate including the read-back.)
+// Rows are applied strictly in site order.
+//
+// Arithmetic: per row the trajectories are handled in groups of G: a group is skipped with one
+// uniform branch when none of its members flipped the site, otherwise every member runs
+// h += m * q with m in {-1, 0, +1} (m = 0 leaves h unchanged).  Returns the union mask.
+template <typename T, int NCH, int R, int K, int TH, int G, int DBG = 0>
+__device__ __forceinline__ uint32_t apply_rows(const T *__restrict__ qoff, unsigned char *ring,
+                                               size_t ld, int i0, const uint32_t (&am)[R],
+                                               const uint32_t (&sm)[R],
+                                               Field<T, NCH * Vec16<T>::V> (&h)[R], int tid) {
+  using C = Cfg<T, NCH, R, TH>;
+  using VecT = typename C::VecT;
+  constexpr int V = C::V, CHW = C::CHW;
+  constexpr int ROW_VECS = NCH * TH;  // 16-byte pieces per row
+  static_assert(R % G == 0, "R must be a multiple of the group size");
+
+  uint32_t any = 0;
+#pragma unroll
+  for (int r = 0; r < R; ++r) any |= am[r];
+  if (any == 0) return 0;
+
+  uint32_t pos[R], neg[R], grp[R / G];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    pos[r] = am[r] & ~sm[r];
+    neg[r] = am[r] & sm[r];
+  }
+#pragma unroll
+  for (int g = 0; g < R / G; ++g) {
+    grp[g] = 0;
+#pragma unroll
+    for (int k = 0; k < G; ++k) grp[g] |= am[g * G + k];
+  }
+
+  const T *base = qoff + (size_t)i0 * ld + (size_t)tid * V;
+  VecT *mine = reinterpret_cast<VecT *>(ring) + tid;  // slot s, piece c: mine[s*ROW_VECS + c*TH]
+  const uint32_t mine_s = smem_addr(mine);
+  uint32_t rem_issue = any, rem_apply = any;
+  int slot_w = 0, slot_r = 0;
+
+  auto issue_next = [&]() {
+    if (rem_issue) {
+      const int s = __ffs(rem_issue) - 1;
+      rem_issue &= rem_issue - 1;
+      const T *rp = base + (size_t)s * ld;
+      const uint32_t dst = mine_s + (uint32_t)slot_w * (ROW_VECS * 16);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + c * (TH * 16)),
+                     "l"(rp + c * CHW)
+                     : "memory");
+      slot_w = (slot_w + 1 == K) ? 0 : slot_w + 1;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");  // one group per step, empty or not
+  };
+
+#pragma unroll 1
+  for (int k = 0; k < K - 1; ++k) issue_next();
+#pragma unroll 1
+  while (rem_apply) {
+    issue_next();
+    asm volatile("cp.async.wait_group %0;" ::"n"(K - 1) : "memory");
+    const int s = __ffs(rem_apply) - 1;
+    rem_apply &= rem_apply - 1;
+    const uint32_t bit = 1u << s;
+    T qv[NCH * V];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) vec_unpack<T>(mine[slot_r * ROW_VECS + c * TH], &qv[c * V]);
+    slot_r = (slot_r + 1 == K) ? 0 : slot_r + 1;
+    if (DBG == 1) {  // timing experiment: touch the data, skip the arithmetic
+      T acc = (T)0;
+#pragma unroll
+      for (int e = 0; e < NCH * V; ++e) acc += qv[e];
+      if (acc == (T)123456789) h[0].set(0, acc);
+      continue;
+    }
+#pragma unroll
+    for (int g = 0; g < R / G; ++g) {
+      if (grp[g] & bit) {
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+          const int r = g * G + k;
+          const T m = (pos[r] & bit) ? (T)1 : ((neg[r] & bit) ? (T)-1 : (T)0);
+          h[r].axpy(m, qv);
+        }
+      }
+    }
+  }
+  return any;
+}
+
+
+}  // namespace dseq
+}  // namespace osa

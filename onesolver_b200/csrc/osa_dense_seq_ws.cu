@@ -1,0 +1,369 @@
+// osa_dense_seq_ws.cu -- K1s/ws: the dense sequential-sweep kernel with warp-specialised
+// decide/apply overlap (same arithmetic and results as osa_dense_seq.cu, bit for bit).
+//
+// In osa_dense_seq.cu every block of 32 sites runs stage -> P1 decide -> P2 apply back to back,
+// and the decide phase (a latency chain of ballot/shfl/fma steps on one warp per trajectory)
+// leaves the row streaming idle for ~20% of the time.  Here the CTA has two roles:
+//
+//   apply warps  (8 warps, 256 threads, ~224 registers each): own the local fields h[r][:] in
+//                registers and stream/apply the accepted rows of block g  (P2 of osa_dense_seq.cu);
+//   decide warps (4 warps, 128 threads, 56 registers each): run the decisions of block g+1
+//                WHILE block g is being applied.
+//
+// Deciding block g+1 needs h on its 32 columns *after* the rows of block g have been applied,
+// which the apply warps have not finished yet.  The decide warps therefore rebuild those 32
+// values themselves: they start from a snapshot of the columns taken after block g-1 was applied
+// and add the accepted rows of block g restricted to the 32 columns (a 32x32 tile of Q), in site
+// order -- the same fma sequence the apply warps perform on those columns, hence the same bits.
+// One CTA-wide barrier per block hands over {accept masks of block g+1} and {snapshot of the
+// columns of block g+2}; both are double buffered.  Registers are moved between the roles with
+// setmaxnreg (the kernel is launched with 384 threads, 168 registers each).
+#include <cstdlib>
+
+#include "osa_dense_seq.cuh"
+
+namespace osa {
+
+using namespace dseq;
+
+namespace {
+
+constexpr int WS_APPLY_THREADS = 256;
+constexpr int WS_DECIDE_WARPS = 4;
+constexpr int WS_THREADS = WS_APPLY_THREADS + WS_DECIDE_WARPS * 32;
+
+__device__ __forceinline__ void bar_cta() { asm volatile("bar.sync 1, %0;" ::"n"(WS_THREADS) : "memory"); }
+__device__ __forceinline__ void bar_decide() {
+  asm volatile("bar.sync 2, %0;" ::"n"(WS_DECIDE_WARPS * 32) : "memory");
+}
+
+template <typename T, int NCH, int R, int K, int G>
+__global__ void __launch_bounds__(WS_THREADS, 1) k_dense_seq_ws(const DenseParams<T> p) {
+  constexpr int TH = WS_APPLY_THREADS;
+  using C = Cfg<T, NCH, R, TH>;
+  using VecT = typename C::VecT;
+  constexpr int V = C::V, CPT = C::CPT, CHW = C::CHW, NWP = C::NWP;
+  constexpr int TPD = (R + WS_DECIDE_WARPS - 1) / WS_DECIDE_WARPS;  // trajectories per decide warp
+  constexpr int TILE_VECS = 32 * 32 / V;
+
+  extern __shared__ __align__(128) unsigned char s_ring[];  // apply warps: K rows, private slots
+  __shared__ __align__(16) T s_snap[2][R][32];   // columns of block g (parity g&1) after block g-2
+  __shared__ __align__(16) T s_tile_d[32][32];   // diagonal tile of the block being decided
+  __shared__ __align__(16) T s_tile_x[32][32];   // rows of the previous block x columns of this one
+  __shared__ uint32_t s_acc[2][R];               // accept / sign masks of block g (parity g&1)
+  __shared__ uint32_t s_sign[2][R];
+  __shared__ uint32_t s_x[R][NWP];
+  __shared__ uint32_t s_xb[R][NWP];
+
+  const int tid = threadIdx.x;
+  const int n = p.n;
+  const int nblk = (n + 31) >> 5;
+  const uint64_t batch0 = (uint64_t)blockIdx.x * R;
+  const uint64_t left = p.num_tries - batch0;
+  const int nvalid = left < (uint64_t)R ? (int)left : R;
+  const long long total_blocks = (long long)p.num_iter * p.sweeps_per_beta * nblk;
+
+  if (tid < WS_APPLY_THREADS) {
+    // =============================== APPLY ROLE ===============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    Field<T, CPT> h[R];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      T dv[V];
+      const VecT v = *reinterpret_cast<const VecT *>(p.diag + c * CHW + tid * V);
+      vec_unpack<T>(v, dv);
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int e = 0; e < V; ++e) h[r].set(c * V + e, dv[e]);
+    }
+    // snapshot of the 32 columns of block b into s_snap[par]
+    auto snapshot = [&](int b, int par) {
+      const int i0 = b * 32;
+      const int cb = i0 / CHW;
+      const int rel = tid * V - (i0 % CHW);
+      if (rel >= 0 && rel < 32) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          if (c == cb) {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+              for (int e = 0; e < V; ++e) s_snap[par][r][rel + e] = h[r].get(c * V + e);
+          }
+        }
+      }
+    };
+    unsigned long long cnt_rows = 0, cnt_init_rows = 0;
+    long long t_apply = 0, t_wait = 0, t_init = 0, t_mark = clock64();
+    auto lap = [&](long long &acc) {
+      const long long now = clock64();
+      acc += now - t_mark;
+      t_mark = now;
+    };
+
+    bar_cta();  // #0: initial spins are in s_x
+    for (int b = 0; b < nblk; ++b) {
+      uint32_t am[R], sm[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        am[r] = s_x[r][b];
+        sm[r] = 0u;
+      }
+      const uint32_t any = apply_rows<T, NCH, R, K, TH, G>(p.qoff, s_ring, p.ld, b * 32, am, sm, h, tid);
+      cnt_init_rows += (unsigned)__popc(any);
+    }
+    snapshot(0, 0);
+    snapshot(nblk > 1 ? 1 : 0, 1);
+    lap(t_init);
+    bar_cta();  // B(-1): snapshots of blocks 0 and 1 are ready
+    bar_cta();  // B(0) : masks of block 0 are ready
+    lap(t_wait);
+    int b = 0;
+    for (long long g = 0; g < total_blocks; ++g) {
+      const int par = (int)(g & 1);
+      uint32_t am[R], sm[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        am[r] = s_acc[par][r];
+        sm[r] = s_sign[par][r];
+      }
+      const uint32_t any = apply_rows<T, NCH, R, K, TH, G>(p.qoff, s_ring, p.ld, b * 32, am, sm, h, tid);
+      cnt_rows += (unsigned)__popc(any);
+      lap(t_apply);
+      if (g + 1 < total_blocks) {
+        // columns of block g+2 as they are now (after block g): consumed by the decision of g+2
+        int b2 = b + 2;
+        if (b2 >= nblk) b2 -= nblk;
+        if (b2 >= nblk) b2 -= nblk;  // nblk == 1
+        snapshot(b2, par);
+        bar_cta();  // B(g+1)
+        lap(t_wait);
+      }
+      b = (b + 1 == nblk) ? 0 : b + 1;
+    }
+    if (tid == 0) {
+      atomicAdd(&p.counters->row_fetches, cnt_rows);
+      atomicAdd(&p.counters->init_row_fetches, cnt_init_rows);
+      atomicAdd(&p.counters->cyc_apply, (unsigned long long)t_apply);
+      atomicAdd(&p.counters->cyc_stage, (unsigned long long)t_wait);
+      atomicAdd(&p.counters->cyc_init, (unsigned long long)t_init);
+    }
+  } else {
+    // =============================== DECIDE ROLE ===============================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    const int dt = tid - WS_APPLY_THREADS;  // 0..127
+    const int lane = dt & 31, dwarp = dt >> 5;
+
+    // initial spins (replaces random.bit(), annealing.hpp:90-92)
+#pragma unroll 1
+    for (int rr = 0; rr < TPD; ++rr) {
+      const int r = dwarp + rr * WS_DECIDE_WARPS;
+      if (r < R) {
+        const bool tv = r < nvalid;
+        const uint64_t traj = p.first_try + batch0 + (uint64_t)r;
+        for (int k = lane; k < NWP; k += 32) {
+          uint32_t word = 0;
+          if (tv && k < nblk) {
+            const U4 d = engine_draw(p.seed, traj, STREAM_INIT, (uint32_t)k >> 2, 0u);
+            word = pick(d, (uint32_t)k & 3u);
+            const int valid = n - k * 32;
+            if (valid < 32) word &= (1u << valid) - 1u;
+          }
+          s_x[r][k] = word;
+          s_xb[r][k] = word;
+        }
+      }
+    }
+    double erel[TPD], best[TPD];
+    bool at_best[TPD];
+#pragma unroll
+    for (int rr = 0; rr < TPD; ++rr) {
+      erel[rr] = 0.0;
+      best[rr] = 0.0;
+      at_best[rr] = true;
+    }
+    unsigned long long cnt_acc = 0;
+    long long t_decide = 0;
+
+    bar_cta();  // #0
+    bar_cta();  // B(-1): snapshots 0 and 1 ready
+
+    // decision of block (iter, sw, b) = global block g; prev_valid: block g-1 exists
+    auto decide = [&](long long g, int b, uint32_t step, T ts) {
+      const int par = (int)(g & 1);
+      const int i0 = b * 32;
+      const int bp = (b == 0) ? nblk - 1 : b - 1;  // previous block (cyclic)
+      // stage the two tiles: diagonal tile of block b, and rows of block bp x columns of block b
+      for (int qi = dt; qi < TILE_VECS; qi += WS_DECIDE_WARPS * 32) {
+        const int row = qi / (32 / V), cv = qi % (32 / V);
+        *reinterpret_cast<VecT *>(&s_tile_d[row][cv * V]) =
+            __ldg(reinterpret_cast<const VecT *>(p.qoff + (size_t)(i0 + row) * p.ld + i0 + cv * V));
+        if (g > 0)
+          *reinterpret_cast<VecT *>(&s_tile_x[row][cv * V]) = __ldg(reinterpret_cast<const VecT *>(
+              p.qoff + (size_t)(bp * 32 + row) * p.ld + i0 + cv * V));
+      }
+      bar_decide();
+#pragma unroll 1
+      for (int rr = 0; rr < TPD; ++rr) {
+        const int r = dwarp + rr * WS_DECIDE_WARPS;
+        if (r < R) {
+          const bool tv = r < nvalid;
+          const uint64_t traj = p.first_try + batch0 + (uint64_t)r;
+          const int site = i0 + lane;
+          T hl = s_snap[par][r][lane];
+          if (g > 0) {
+            // bring the snapshot up to date: rows of block g-1 that this trajectory flipped
+            uint32_t pa = s_acc[par ^ 1][r];
+            const uint32_t ps = s_sign[par ^ 1][r];
+            while (pa) {
+              const int s = __ffs(pa) - 1;
+              pa &= pa - 1;
+              const T sgn = ((ps >> s) & 1u) ? (T)-1 : (T)1;
+              hl = det::fma(sgn, s_tile_x[s][lane], hl);
+            }
+          }
+          uint32_t xw = s_x[r][b];
+          const U4 d = engine_draw(p.seed, traj, STREAM_SEQ, (uint32_t)site >> 2, step);
+          const T theta = threshold<T>(ts, pick(d, (uint32_t)site & 3u));
+          const bool lane_ok = tv && site < n;
+          uint32_t acc = 0, sg = 0, from = 0xffffffffu;
+          for (;;) {
+            const uint32_t xl = (xw >> lane) & 1u;
+            const T dEl = xl ? -hl : hl;
+            const uint32_t bal = __ballot_sync(0xffffffffu, lane_ok && (dEl < theta)) & from;
+            if (bal == 0) break;
+            const int s = __ffs(bal) - 1;
+            const T dEs = __shfl_sync(0xffffffffu, dEl, s);
+            const uint32_t xbit = (xw >> s) & 1u;
+            const T sgn = xbit ? (T)-1 : (T)1;
+            hl = det::fma(sgn, s_tile_d[s][lane], hl);
+            const double e = det::add(erel[rr], (double)dEs);
+            erel[rr] = e;
+            if (e < best[rr]) {
+              best[rr] = e;
+              at_best[rr] = true;
+            } else if (at_best[rr]) {
+              // leaving the best state: snapshot the state as it was BEFORE this flip
+              for (int k = lane; k < nblk; k += 32) s_xb[r][k] = s_x[r][k];
+              __syncwarp();
+              if (lane == 0) s_xb[r][b] = xw;
+              __syncwarp();
+              at_best[rr] = false;
+            }
+            xw ^= (1u << s);
+            acc |= (1u << s);
+            sg |= (xbit << s);
+            from = (s == 31) ? 0u : (0xffffffffu << (s + 1));
+          }
+          if (lane == 0) {
+            s_x[r][b] = xw;
+            s_acc[par][r] = acc;
+            s_sign[par][r] = sg;
+            cnt_acc += (unsigned)__popc(acc);
+          }
+        }
+      }
+      bar_decide();  // the tiles may be overwritten by the next call
+    };
+
+    long long g = 0;
+    uint32_t step = 0;
+    long long t_mark = clock64();
+    for (int iter = 0; iter < p.num_iter; ++iter) {
+      const T ts = p.tscale[iter];
+      for (int sw = 0; sw < p.sweeps_per_beta; ++sw, ++step) {
+        for (int b = 0; b < nblk; ++b, ++g) {
+          decide(g, b, step, ts);
+          t_decide += clock64() - t_mark;
+          bar_cta();  // B(g): masks of block g ready (g = 0: the apply warps have been waiting)
+          t_mark = clock64();
+        }
+      }
+    }
+    // ---- results ----
+#pragma unroll 1
+    for (int rr = 0; rr < TPD; ++rr) {
+      const int r = dwarp + rr * WS_DECIDE_WARPS;
+      if (r < R && r < nvalid) {
+        if (at_best[rr]) {
+          for (int k = lane; k < nblk; k += 32) s_xb[r][k] = s_x[r][k];
+        }
+        __syncwarp();
+        const uint64_t tl = batch0 + (uint64_t)r;
+        for (int k = lane; k < p.nw; k += 32) p.best_states[tl * (uint64_t)p.nw + k] = s_xb[r][k];
+        if (lane == 0) p.best_rel[tl] = best[rr];
+      }
+    }
+    if (lane == 0) {
+      if (cnt_acc) atomicAdd(&p.counters->accepts, cnt_acc);
+      if (dwarp == 0) atomicAdd(&p.counters->cyc_decide, (unsigned long long)t_decide);
+    }
+  }
+}
+
+template <typename T, int NCH, int R, int K, int G>
+cudaError_t launch_ws(const DenseParams<T> &p, cudaStream_t s, LaunchInfo *info) {
+  const uint64_t grid64 = (p.num_tries + R - 1) / R;
+  if (grid64 == 0 || grid64 > 0x7fffffffull) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)K * NCH * WS_APPLY_THREADS * 16;
+  auto kern = k_dense_seq_ws<T, NCH, R, K, G>;
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  kern<<<(unsigned)grid64, WS_THREADS, smem, s>>>(p);
+  if (info) {
+    info->grid = (int)grid64;
+    info->block = WS_THREADS;
+    info->traj_per_batch = R;
+    info->smem = smem;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+// same shape table as launch_dense_seq (osa_dense_seq.cu)
+template <typename T>
+cudaError_t launch_dense_seq_ws(const DenseParams<T> &p, cudaStream_t s, LaunchInfo *info);
+
+template <>
+cudaError_t launch_dense_seq_ws<float>(const DenseParams<float> &p, cudaStream_t s,
+                                       LaunchInfo *info) {
+  if (p.ld % 1024 != 0) return cudaErrorInvalidValue;
+  switch (p.ld / 1024) {
+    case 1: return launch_ws<float, 1, 16, 16, 4>(p, s, info);
+    case 2: return launch_ws<float, 2, 16, 16, 4>(p, s, info);
+    case 3: return launch_ws<float, 3, 12, 12, 4>(p, s, info);
+    case 4: {
+      const char *e = getenv("OSA_WS_R");  // tuning knob (tools/probe.py): trajectories per CTA
+      const int r = e ? atoi(e) : 12;
+      if (r == 8) return launch_ws<float, 4, 8, 12, 1>(p, s, info);
+      if (r == 10) return launch_ws<float, 4, 10, 12, 1>(p, s, info);
+      return launch_ws<float, 4, 12, 12, 2>(p, s, info);  // measured best (profiles/r01)
+    }
+    case 5: return launch_ws<float, 5, 8, 9, 2>(p, s, info);
+    case 6: return launch_ws<float, 6, 8, 8, 2>(p, s, info);
+    case 7: return launch_ws<float, 7, 4, 6, 2>(p, s, info);
+    case 8: return launch_ws<float, 8, 4, 6, 2>(p, s, info);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+template <>
+cudaError_t launch_dense_seq_ws<double>(const DenseParams<double> &p, cudaStream_t s,
+                                        LaunchInfo *info) {
+  if (p.ld % 512 != 0) return cudaErrorInvalidValue;
+  switch (p.ld / 512) {
+    case 1: return launch_ws<double, 1, 16, 16, 4>(p, s, info);
+    case 2: return launch_ws<double, 2, 16, 16, 4>(p, s, info);
+    case 3: return launch_ws<double, 3, 12, 12, 4>(p, s, info);
+    case 4: return launch_ws<double, 4, 8, 12, 2>(p, s, info);
+    case 5: return launch_ws<double, 5, 6, 9, 2>(p, s, info);
+    case 6: return launch_ws<double, 6, 6, 8, 2>(p, s, info);
+    case 7: return launch_ws<double, 7, 4, 6, 2>(p, s, info);
+    case 8: return launch_ws<double, 8, 4, 6, 2>(p, s, info);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace osa

@@ -70,6 +70,14 @@ if "cfg" in what:
         run_dense(4096, capi.SWEEP_F32, 148 * r, 4, 0.3 * s, 0.02 * s, "cfg%s_hot2cold" % cfg)
     os.environ.pop("OSA_DS_CFG")
 
+if "wsr" in what:
+    import os
+    s = np.sqrt(4096)
+    for r, key in ((8, "8"), (10, "10"), (12, "12")):
+        os.environ["OSA_WS_R"] = key
+        run_dense(4096, capi.SWEEP_F32, 148 * r, 4, 0.3 * s, 0.02 * s, "ws_R%s_hot2cold" % key)
+    os.environ.pop("OSA_WS_R")
+
 if "sparse" in what:
     n = 5627
     rowptr, col, val, diag = gen.sparse_random_graph(n, 15, seed=2028)
