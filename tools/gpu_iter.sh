@@ -7,7 +7,7 @@ tail -3 gpurun_out/pytest_$TAG.log
 timeout 600 python tools/probe.py dense sparse > gpurun_out/probe_$TAG.log 2>&1; cat gpurun_out/probe_$TAG.log
 if [ "$PROF" = "1" ]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_dense_seq -c 1 \
-    -o gpurun_out/prof_dense_seq_$TAG python bench.py --steps 1 --warmup 0 --tries-per-gpu 1184 --sweeps 2 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full_$TAG.log 2>&1
+    -o gpurun_out/prof_dense_seq_$TAG python bench.py --steps 1 --warmup 0 --tries-per-gpu 1776 --sweeps 2 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full_$TAG.log 2>&1
   tail -2 gpurun_out/ncu_full_$TAG.log | cut -c1-300
 fi
 if [ "$PROF" = "2" ]; then
