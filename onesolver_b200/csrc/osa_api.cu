@@ -533,6 +533,8 @@ int osa_anneal(osa_problem *p, const double *beta_schedule, const osa_anneal_par
       sp.best_rel = p->d_best_rel;
       sp.best_states = p->d_states;
       sp.xbest_ws = p->d_xbest_ws;
+      sp.debug_flags = 0;
+      sp.log_base = 0;
       sp.nw = p->nw;
       sp.counters = p->d_counters;
       return launch_sparse<T>(sp, p->stream, &info);

@@ -170,6 +170,8 @@ struct SparseParams {
   double *best_rel;
   uint32_t *best_states;  // [num_tries][nw]
   uint32_t *xbest_ws;     // [n_warps_total][n] transposed best-state workspace
+  size_t log_base;        // word offset of the flip logs inside xbest_ws (set by the launcher)
+  int debug_flags;        // timing experiments only (tools/probe.py): 1 = skip best-state snapshots
   int nw;
   Counters *counters;
 };

@@ -10,18 +10,39 @@
 // O(N^2)-per-attempt kernel (/root/reference/include/simulated_annealing/
 // annealing.hpp:85-126) for sparse instances; the reference itself has no sparse path.
 //
-// Best-state tracking (annealing.hpp:115-121) is lazy: the transposed best state XB
-// (global workspace) is only rewritten, for the lanes concerned, when a trajectory
-// LEAVES its best state.
+// Best-state tracking (annealing.hpp:115-121, strict improvement) without copying states:
+// when a trajectory leaves its best state it starts a short per-lane LOG of the sites it
+// flips; the best state is then (current state) XOR (logged flips).  A new best clears the
+// log.  Only when an excursion outgrows the log (SP_LOG entries) is the best state written
+// out to the transposed workspace XB (one warp-cooperative column copy + the logged toggles),
+// after which logging stops until the next new best.  Short excursions -- the common case
+// while the walk descends -- therefore cost one 2-byte store per flip instead of an O(N) copy.
+#include <cstdlib>
+
 #include "osa_common.cuh"
 
 namespace osa {
 
 namespace {
 
+// CSR entries of one block of 32 consecutive sites, staged per warp in shared memory
+constexpr int SP_LOG = 64;   // flips remembered per trajectory after leaving a best state
+constexpr int SP_CAP = 512;  // entries per staging buffer (32 sites x degree 16); larger blocks
+                             // fall back to direct global loads
+
 template <typename T>
-__global__ void k_sparse(const SparseParams<T> p) {
-  extern __shared__ uint32_t smem_x[];
+struct SpStage {
+  int32_t col[2][SP_CAP];
+  T val[2][SP_CAP];
+};
+
+__device__ __forceinline__ uint32_t sp_smem_addr(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+template <typename T>
+__global__ void k_sparse(const SparseParams<T> p, int x_words_per_warp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const uint64_t gw = (uint64_t)blockIdx.x * wpb + warp;
   const uint64_t tl0 = gw * 32ull;
@@ -31,7 +52,10 @@ __global__ void k_sparse(const SparseParams<T> p) {
   const uint64_t traj = p.first_try + tl;
   const int n = p.n;
 
-  uint32_t *X = smem_x + (size_t)warp * n;
+  // shared memory: [wpb] staging structs, then [wpb][x_words_per_warp] spin words
+  SpStage<T> *stage = reinterpret_cast<SpStage<T> *>(smem_raw) + warp;
+  uint32_t *X = reinterpret_cast<uint32_t *>(smem_raw + (size_t)wpb * sizeof(SpStage<T>)) +
+                (size_t)warp * x_words_per_warp;
   uint32_t *XB = p.xbest_ws + gw * (uint64_t)n;
 
   // initial spins: lane draws its own packed word, the warp transposes it with ballots
@@ -53,57 +77,152 @@ __global__ void k_sparse(const SparseParams<T> p) {
   __syncwarp();
 
   double erel = 0.0, best = 0.0;
-  bool at_best = true;
+  bool at_best = true;   // the current state IS the best state
+  bool mat = false;      // XB holds the best state explicitly (no log needed)
+  int log_len = 0;       // flips since the best state was left (valid while !at_best && !mat)
   unsigned long long cnt_acc = 0;
+  // per-warp flip log in the workspace behind the N words of XB: [SP_LOG][32] uint16
+  uint16_t *LOG = reinterpret_cast<uint16_t *>(p.xbest_ws + p.log_base) + gw * (uint64_t)(SP_LOG * 32);
 
-  // lanes in `leaving` drop out of their best state: copy their (pre-flip) bits to XB
-  auto snapshot = [&](uint32_t leaving) {
-    for (int j = lane; j < n; j += 32) XB[j] = (XB[j] & ~leaving) | (X[j] & leaving);
+  // write the best states of the lanes in `who` to XB: their column of X (the state BEFORE the
+  // current step's flips) with the logged flips undone
+  auto materialize = [&](uint32_t who, bool use_log) {
+    if (p.debug_flags & 1) return;
+    for (int j = lane; j < n; j += 32) XB[j] = (XB[j] & ~who) | (X[j] & who);
+    __syncwarp();
+    if (use_log && ((who >> lane) & 1u)) {
+      for (int e = 0; e < log_len; ++e) atomicXor(&XB[LOG[e * 32 + lane]], 1u << lane);
+    }
+    __syncwarp();
+  };
+  // bookkeeping of one accepted flip of `site` with energy change dE (call BEFORE X is updated);
+  // returns true when this lane's log overflowed and its best state must be materialised
+  auto track = [&](int site, T dE) -> bool {
+    const double e = det::add(erel, (double)dE);
+    erel = e;
+    ++cnt_acc;
+    if (e < best) {
+      best = e;
+      at_best = true;
+      mat = false;
+      log_len = 0;
+      return false;
+    }
+    if (at_best) {  // leaving the best state: it equals the state before this flip
+      at_best = false;
+      mat = false;
+      log_len = 0;
+    }
+    if (mat) return false;
+    if (log_len < SP_LOG) {
+      LOG[log_len * 32 + lane] = (uint16_t)site;
+      ++log_len;
+      return false;
+    }
+    return true;
   };
 
   if (p.mode == OSA_MODE_SEQUENTIAL_SWEEP) {
+    // The CSR arrays (~10 bytes per neighbour) live in L2; reading them with dependent loads
+    // would put 2-3 L2 round trips on every site.  Instead the entries of the NEXT block of 32
+    // sites are copied into a per-warp shared-memory buffer with cp.async while the current
+    // block is processed (double buffer), and rowptr/diag of the next block are prefetched into
+    // registers, so the per-site critical path only touches shared memory.
+    const int nblk = (n + 31) >> 5;
+    auto block_range = [&](int b, int &e0, int &e1) {
+      e0 = __ldg(p.rowptr + b * 32);
+      e1 = __ldg(p.rowptr + min(b * 32 + 32, n));
+    };
+    auto prefetch_entries = [&](int b, int buf) {  // always commits one group
+      int e0, e1;
+      block_range(b, e0, e1);
+      if (e1 - e0 <= SP_CAP) {
+        for (int q = e0 + lane; q < e1; q += 32) {
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(
+                           sp_smem_addr(&stage->col[buf][q - e0])),
+                       "l"(p.col + q)
+                       : "memory");
+          asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(
+                           sp_smem_addr(&stage->val[buf][q - e0])),
+                       "l"(p.val + q), "n"((int)sizeof(T))
+                       : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto load_meta = [&](int b, int &rp_lo, int &rp_hi, T &dg) {
+      const int i = b * 32 + lane;
+      rp_lo = __ldg(p.rowptr + min(i, n));
+      rp_hi = __ldg(p.rowptr + min(i + 1, n));
+      dg = (i < n) ? __ldg(p.diag + i) : (T)0;
+    };
+
+    int rp_lo, rp_hi, nrp_lo, nrp_hi;
+    T dg, ndg;
+    prefetch_entries(0, 0);
+    load_meta(0, rp_lo, rp_hi, dg);
+    long long gblock = 0;
     uint32_t step = 0;
     for (int iter = 0; iter < p.num_iter; ++iter) {
       const T ts = p.tscale[iter];
       for (int sw = 0; sw < p.sweeps_per_beta; ++sw, ++step) {
         U4 d = U4{0, 0, 0, 0};
-        for (int i = 0; i < n; ++i) {
-          if ((i & 3) == 0) d = engine_draw(p.seed, traj, STREAM_SEQ, (uint32_t)i >> 2, step);
-          const T theta = threshold<T>(ts, pick(d, (uint32_t)i & 3u));
-          T hk = __ldg(p.diag + i);
-          const int pb = __ldg(p.rowptr + i), pe = __ldg(p.rowptr + i + 1);
-          for (int q = pb; q < pe; ++q) {
-            const int c = __ldg(p.col + q);
-            const T v = __ldg(p.val + q);
-            if ((X[c] >> lane) & 1u) hk = det::add(hk, v);
-          }
-          const uint32_t xiw = X[i];
-          const T dE = ((xiw >> lane) & 1u) ? -hk : hk;
-          const bool acc = tv && (dE < theta);
-          bool leave = false;
-          if (acc) {
-            const double e = det::add(erel, (double)dE);
-            erel = e;
-            ++cnt_acc;
-            if (e < best) {
-              best = e;
-              at_best = true;
-            } else if (at_best) {
-              leave = true;
-              at_best = false;
+        for (int b = 0; b < nblk; ++b, ++gblock) {
+          const int buf = (int)(gblock & 1);
+          const int bn = (b + 1 == nblk) ? 0 : b + 1;  // next block (wraps into the next sweep)
+          prefetch_entries(bn, buf ^ 1);
+          load_meta(bn, nrp_lo, nrp_hi, ndg);
+          asm volatile("cp.async.wait_group 1;" ::: "memory");  // this block's entries landed
+          __syncwarp();
+          const int e0 = __shfl_sync(0xffffffffu, rp_lo, 0);
+          const int e1 = __shfl_sync(0xffffffffu, rp_hi, min(31, n - b * 32 - 1));
+          const bool staged = (e1 - e0) <= SP_CAP;
+          const int i_end = min(32, n - b * 32);
+          for (int s = 0; s < i_end; ++s) {
+            const int i = b * 32 + s;
+            if ((i & 3) == 0) d = engine_draw(p.seed, traj, STREAM_SEQ, (uint32_t)i >> 2, step);
+            const T theta = threshold<T>(ts, pick(d, (uint32_t)i & 3u));
+            const int pb = __shfl_sync(0xffffffffu, rp_lo, s);
+            const int pe = __shfl_sync(0xffffffffu, rp_hi, s);
+            T hk = __shfl_sync(0xffffffffu, dg, s);
+            if (staged) {
+              const int32_t *sc = stage->col[buf] - e0;
+              const T *sv = stage->val[buf] - e0;
+#pragma unroll 4
+              for (int q = pb; q < pe; ++q) {
+                if ((X[sc[q]] >> lane) & 1u) hk = det::add(hk, sv[q]);
+              }
+            } else {
+              for (int q = pb; q < pe; ++q) {
+                const int c = __ldg(p.col + q);
+                const T v = __ldg(p.val + q);
+                if ((X[c] >> lane) & 1u) hk = det::add(hk, v);
+              }
+            }
+            const uint32_t xiw = X[i];
+            const T dE = ((xiw >> lane) & 1u) ? -hk : hk;
+            const bool acc = tv && (dE < theta);
+            const bool overflow = acc ? track(i, dE) : false;
+            const uint32_t spill = __ballot_sync(0xffffffffu, overflow);
+            if (spill) {
+              materialize(spill, true);
+              if (overflow) mat = true;
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, acc);
+            if (bal) {
+              __syncwarp();
+              if (lane == 0) X[i] = xiw ^ bal;
+              __syncwarp();
             }
           }
-          const uint32_t leaving = __ballot_sync(0xffffffffu, leave);
-          if (leaving) snapshot(leaving);
-          const uint32_t bal = __ballot_sync(0xffffffffu, acc);
-          if (bal) {
-            __syncwarp();
-            if (lane == 0) X[i] = xiw ^ bal;
-            __syncwarp();
-          }
+          rp_lo = nrp_lo;
+          rp_hi = nrp_hi;
+          dg = ndg;
+          __syncwarp();  // everyone is done with stage buffer `buf` before it is refilled
         }
       }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else {
     const uint64_t total = (uint64_t)p.num_iter * (uint64_t)p.sweeps_per_beta;
     for (uint64_t st = 0; st < total; ++st) {
@@ -121,29 +240,25 @@ __global__ void k_sparse(const SparseParams<T> p) {
       }
       const T dE = ((X[k] >> lane) & 1u) ? -hk : hk;
       const bool acc = tv && (dE < theta);
-      bool leave = false;
-      if (acc) {
-        const double e = det::add(erel, (double)dE);
-        erel = e;
-        ++cnt_acc;
-        if (e < best) {
-          best = e;
-          at_best = true;
-        } else if (at_best) {
-          leave = true;
-          at_best = false;
-        }
+      const bool overflow = acc ? track(k, dE) : false;
+      const uint32_t spill = __ballot_sync(0xffffffffu, overflow);
+      if (spill) {
+        materialize(spill, true);
+        if (overflow) mat = true;
       }
-      const uint32_t leaving = __ballot_sync(0xffffffffu, leave);
-      if (leaving) snapshot(leaving);
       __syncwarp();
       if (acc) atomicXor(&X[k], 1u << lane);
       __syncwarp();
     }
   }
 
-  const uint32_t still = __ballot_sync(0xffffffffu, at_best);
-  if (still) snapshot(still);
+  // final best states: current state (at_best), current state with the log undone, or XB as is
+  {
+    const uint32_t cur = __ballot_sync(0xffffffffu, at_best);
+    if (cur) materialize(cur, false);
+    const uint32_t logged = __ballot_sync(0xffffffffu, !at_best && !mat);
+    if (logged) materialize(logged, true);
+  }
   __syncwarp();
 
   // un-transpose: lane assembles its own packed words
@@ -166,8 +281,12 @@ __global__ void k_sparse(const SparseParams<T> p) {
 
 constexpr size_t kMaxSmem = 227 * 1024;
 
-int pick_wpb(int n, uint64_t num_tries, int sm_count) {
-  const size_t per_warp = (size_t)n * sizeof(uint32_t);
+template <typename T>
+size_t sp_per_warp_bytes(int n) {
+  return sizeof(SpStage<T>) + (size_t)((n + 3) / 4 * 4) * sizeof(uint32_t);
+}
+
+int pick_wpb(size_t per_warp, uint64_t num_tries, int sm_count) {
   int wpb_max = (int)(kMaxSmem / per_warp);
   if (wpb_max < 1) return 0;
   if (wpb_max > 8) wpb_max = 8;
@@ -189,16 +308,24 @@ cudaError_t launch_impl(const SparseParams<T> &p, cudaStream_t s, LaunchInfo *in
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int wpb = pick_wpb(p.n, p.num_tries, sms);
+  const size_t per_warp = sp_per_warp_bytes<T>(p.n);
+  SparseParams<T> pp = p;
+  pp.log_base = (size_t)((p.num_tries + 31) / 32) * (size_t)p.n;  // words; see sparse_ws_words
+  {
+    const char *e = getenv("OSA_SP_DEBUG");
+    pp.debug_flags = e ? atoi(e) : 0;
+  }
+  const int wpb = pick_wpb(per_warp, p.num_tries, sms);
   if (wpb < 1) return cudaErrorInvalidValue;
-  const size_t smem = (size_t)wpb * p.n * sizeof(uint32_t);
+  const size_t smem = (size_t)wpb * per_warp;
+  const int x_words = (p.n + 3) / 4 * 4;
   cudaError_t err =
       cudaFuncSetAttribute(k_sparse<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
   const uint64_t warps = (p.num_tries + 31) / 32;
   const uint64_t grid64 = (warps + wpb - 1) / wpb;
   if (grid64 == 0 || grid64 > 0x7fffffffull) return cudaErrorInvalidValue;
-  k_sparse<T><<<(unsigned)grid64, wpb * 32, smem, s>>>(p);
+  k_sparse<T><<<(unsigned)grid64, wpb * 32, smem, s>>>(pp, x_words);
   if (info) {
     info->grid = (int)grid64;
     info->block = wpb * 32;
@@ -211,8 +338,10 @@ cudaError_t launch_impl(const SparseParams<T> &p, cudaStream_t s, LaunchInfo *in
 }  // namespace
 
 size_t sparse_ws_words(int n, uint64_t num_tries) {
-  // one transposed best-state array per warp; warps are indexed by gw = tl0/32 regardless of wpb
-  return (size_t)((num_tries + 31) / 32) * (size_t)n;
+  // per warp (gw = tl0/32, independent of the CTA shape): N words of transposed best state, and
+  // behind all of those the flip logs, SP_LOG*32 uint16 = SP_LOG*16 words per warp
+  const size_t warps = (size_t)((num_tries + 31) / 32);
+  return warps * (size_t)n + warps * (size_t)(SP_LOG * 16);
 }
 
 template <>

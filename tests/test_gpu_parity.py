@@ -278,3 +278,18 @@ def test_cli_gpu_paths(gpu, tmp_path):
                        capture_output=True, text=True, cwd=root)
     assert r.returncode == 0, r.stderr
     assert ex.read_text() == "0,1,2,3,4,5,6,7,8,9,10,11,12,energy\n1,1,1,0,1,1,0,0,0,0,0,0,0,-32\n"
+
+
+@pytest.mark.parametrize("n,dtype,tries", [(200, np.float32, 30), (1100, np.float32, 17),
+                                           (513, np.float64, 20), (4096, np.float32, 13)])
+def test_single_role_kernel_is_bit_identical_to_warp_specialised(gpu, monkeypatch, n, dtype, tries):
+    """OSA_DS_WS=0 selects k_dense_seq (decide and apply back to back); the default k_dense_seq_ws
+    overlaps them.  Both must walk exactly the trajectories of the host replay."""
+    q = gen.dense_uniform_qubo(n, seed=300 + n)
+    scale = np.sqrt(n)
+    sched = geo(3, 0.02 * scale, 0.6 * scale)
+    a, _ = run_and_compare_dense(q, sched, 3, tries, capi.MODE_SEQUENTIAL_SWEEP, dtype)
+    monkeypatch.setenv("OSA_DS_WS", "0")
+    b, _ = run_and_compare_dense(q, sched, 3, tries, capi.MODE_SEQUENTIAL_SWEEP, dtype)
+    np.testing.assert_array_equal(a.best_states_packed, b.best_states_packed)
+    assert a.stats["grid"] != 0 and b.stats["grid"] != 0
