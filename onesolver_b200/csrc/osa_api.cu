@@ -93,6 +93,29 @@ namespace {
 
 size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
 
+// Device memory comes from the stream-ordered allocator with an unlimited release threshold, so
+// the create -> anneal -> destroy cycle of one sa::anneal call reuses pooled memory instead of
+// paying cudaMalloc/cudaFree (tens of milliseconds for the 64-128 MiB arrays) every time.
+void keep_pool_memory(int device) {
+  static bool done[64] = {false};
+  if (device < 0 || device >= 64 || done[device]) return;
+  cudaMemPool_t pool = nullptr;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    unsigned long long threshold = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+  }
+  done[device] = true;
+}
+
+template <typename P>
+cudaError_t dev_alloc(P **ptr, size_t bytes, cudaStream_t stream) {
+  return cudaMallocAsync(reinterpret_cast<void **>(ptr), bytes, stream);
+}
+template <typename P>
+void dev_free(P *ptr, cudaStream_t stream) {
+  if (ptr) cudaFreeAsync(const_cast<void *>(static_cast<const void *>(ptr)), stream);
+}
+
 // build the sweep-precision layouts from a dense upload
 template <typename TIn, typename T>
 __global__ void k_prep_dense(const TIn *__restrict__ in, int n, T *__restrict__ qoff, size_t ld,
@@ -134,9 +157,10 @@ __global__ void k_convert(const double *__restrict__ in, T *__restrict__ out, si
 int init_exec(osa_problem *p) {
   CUDA_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
   for (auto &e : p->ev) CUDA_TRY(cudaEventCreate(&e));
-  CUDA_TRY(cudaMalloc(&p->d_counters, sizeof(Counters)));
-  CUDA_TRY(cudaMalloc(&p->d_arg_idx, sizeof(unsigned long long)));
-  CUDA_TRY(cudaMalloc(&p->d_arg_e, sizeof(double)));
+  keep_pool_memory(p->device);
+  CUDA_TRY(dev_alloc(&p->d_counters, sizeof(Counters), p->stream));
+  CUDA_TRY(dev_alloc(&p->d_arg_idx, sizeof(unsigned long long), p->stream));
+  CUDA_TRY(dev_alloc(&p->d_arg_e, sizeof(double), p->stream));
   return OSA_OK;
 }
 
@@ -185,8 +209,8 @@ int create_dense(const TIn *qsym, int n, int device, int prec, osa_problem **out
   do {                                                                                       \
     cudaError_t _e = (expr);                                                                 \
     if (_e != cudaSuccess) {                                                                 \
-      if (d_in) cudaFree(d_in);                                                              \
-      if (d_bad) cudaFree(d_bad);                                                            \
+      dev_free(d_in, p->stream);                                                             \
+      dev_free(d_bad, p->stream);                                                            \
       fail(_e == cudaErrorMemoryAllocation ? OSA_ERR_NOMEM : OSA_ERR_CUDA, "%s failed: %s",  \
            #expr, cudaGetErrorString(_e));                                                   \
       return bail(_e == cudaErrorMemoryAllocation ? OSA_ERR_NOMEM : OSA_ERR_CUDA);           \
@@ -194,11 +218,11 @@ int create_dense(const TIn *qsym, int n, int device, int prec, osa_problem **out
   } while (0)
 
   const size_t total = (size_t)n * n;
-  TRY_B(cudaMalloc(&d_in, total * sizeof(TIn)));
-  TRY_B(cudaMalloc(&d_bad, sizeof(int)));
-  TRY_B(cudaMalloc(&p->d_qoff, p->rows_pad * p->ld * esz));
-  TRY_B(cudaMalloc(&p->d_diag, p->ld * esz));
-  TRY_B(cudaMalloc(&p->d_q64, (size_t)n * p->ld64 * sizeof(double)));
+  TRY_B(dev_alloc(&d_in, total * sizeof(TIn), p->stream));
+  TRY_B(dev_alloc(&d_bad, sizeof(int), p->stream));
+  TRY_B(dev_alloc(&p->d_qoff, p->rows_pad * p->ld * esz, p->stream));
+  TRY_B(dev_alloc(&p->d_diag, p->ld * esz, p->stream));
+  TRY_B(dev_alloc(&p->d_q64, (size_t)n * p->ld64 * sizeof(double), p->stream));
   TRY_B(cudaMemcpyAsync(d_in, qsym, total * sizeof(TIn), cudaMemcpyHostToDevice, p->stream));
   TRY_B(cudaMemsetAsync(d_bad, 0, sizeof(int), p->stream));
   TRY_B(cudaMemsetAsync(p->d_qoff, 0, p->rows_pad * p->ld * esz, p->stream));
@@ -216,8 +240,8 @@ int create_dense(const TIn *qsym, int n, int device, int prec, osa_problem **out
   int bad = 0;
   TRY_B(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
   TRY_B(cudaStreamSynchronize(p->stream));
-  cudaFree(d_in);
-  cudaFree(d_bad);
+  dev_free(d_in, p->stream);
+  dev_free(d_bad, p->stream);
   d_in = nullptr;
   d_bad = nullptr;
 #undef TRY_B
@@ -231,39 +255,39 @@ int create_dense(const TIn *qsym, int n, int device, int prec, osa_problem **out
 
 int ensure_workspace(osa_problem *p, uint64_t num_tries, int num_iter) {
   if (num_tries > p->cap_tries) {
-    if (p->d_best_rel) cudaFree(p->d_best_rel);
-    if (p->d_energy) cudaFree(p->d_energy);
+    dev_free(p->d_best_rel, p->stream);
+    dev_free(p->d_energy, p->stream);
     p->d_best_rel = nullptr;
     p->d_energy = nullptr;
     p->cap_tries = 0;
-    CUDA_TRY(cudaMalloc(&p->d_best_rel, num_tries * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&p->d_energy, num_tries * sizeof(double)));
+    CUDA_TRY(dev_alloc(&p->d_best_rel, num_tries * sizeof(double), p->stream));
+    CUDA_TRY(dev_alloc(&p->d_energy, num_tries * sizeof(double), p->stream));
     p->cap_tries = num_tries;
   }
   const size_t words = (size_t)num_tries * p->nw;
   if (words > p->cap_states_words) {
-    if (p->d_states) cudaFree(p->d_states);
+    dev_free(p->d_states, p->stream);
     p->d_states = nullptr;
     p->cap_states_words = 0;
-    CUDA_TRY(cudaMalloc(&p->d_states, words * sizeof(uint32_t)));
+    CUDA_TRY(dev_alloc(&p->d_states, words * sizeof(uint32_t), p->stream));
     p->cap_states_words = words;
   }
   if (p->sparse) {
     const size_t ws = sparse_ws_words(p->n, num_tries);
     if (ws > p->cap_ws_words) {
-      if (p->d_xbest_ws) cudaFree(p->d_xbest_ws);
+      dev_free(p->d_xbest_ws, p->stream);
       p->d_xbest_ws = nullptr;
       p->cap_ws_words = 0;
-      CUDA_TRY(cudaMalloc(&p->d_xbest_ws, ws * sizeof(uint32_t)));
+      CUDA_TRY(dev_alloc(&p->d_xbest_ws, ws * sizeof(uint32_t), p->stream));
       p->cap_ws_words = ws;
     }
   }
   const size_t tb = (size_t)num_iter * 8;
   if (tb > p->cap_tscale_bytes) {
-    if (p->d_tscale) cudaFree(p->d_tscale);
+    dev_free(p->d_tscale, p->stream);
     p->d_tscale = nullptr;
     p->cap_tscale_bytes = 0;
-    CUDA_TRY(cudaMalloc(&p->d_tscale, tb));
+    CUDA_TRY(dev_alloc(&p->d_tscale, tb, p->stream));
     p->cap_tscale_bytes = tb;
   }
   return OSA_OK;
@@ -372,11 +396,11 @@ int osa_problem_create_csr_f64(const int32_t *rowptr, const int32_t *col, const 
   auto step = [&](cudaError_t r) {
     if (e == cudaSuccess) e = r;
   };
-  step(cudaMalloc(&p->d_rowptr, (size_t)(n + 1) * sizeof(int32_t)));
-  step(cudaMalloc(&p->d_col, nnz_a * sizeof(int32_t)));
-  step(cudaMalloc(&p->d_val64, nnz_a * sizeof(double)));
-  step(cudaMalloc(&p->d_diag64, (size_t)n * sizeof(double)));
-  step(cudaMalloc(&p->d_val, (nnz_a + (size_t)n) * esz));
+  step(dev_alloc(&p->d_rowptr, (size_t)(n + 1) * sizeof(int32_t), p->stream));
+  step(dev_alloc(&p->d_col, nnz_a * sizeof(int32_t), p->stream));
+  step(dev_alloc(&p->d_val64, nnz_a * sizeof(double), p->stream));
+  step(dev_alloc(&p->d_diag64, (size_t)n * sizeof(double), p->stream));
+  step(dev_alloc(&p->d_val, (nnz_a + (size_t)n) * esz, p->stream));
   if (e == cudaSuccess) {
     step(cudaMemcpyAsync(p->d_rowptr, rowptr, (size_t)(n + 1) * sizeof(int32_t),
                          cudaMemcpyHostToDevice, p->stream));
@@ -413,25 +437,27 @@ int osa_problem_create_csr_f64(const int32_t *rowptr, const int32_t *col, const 
 int osa_problem_destroy(osa_problem *p) {
   if (!p) return OSA_OK;
   cudaSetDevice(p->device);
+  cudaStream_t st = p->stream;
   if (p->sparse) {
-    cudaFree(p->d_rowptr);
-    cudaFree(p->d_col);
-    cudaFree(p->d_val);
-    cudaFree(p->d_val64);
-    cudaFree(p->d_diag64);
+    dev_free(p->d_rowptr, st);
+    dev_free(p->d_col, st);
+    dev_free(p->d_val, st);
+    dev_free(p->d_val64, st);
+    dev_free(p->d_diag64, st);
   } else {
-    cudaFree(p->d_qoff);
-    cudaFree(p->d_diag);
-    cudaFree(p->d_q64);
+    dev_free(p->d_qoff, st);
+    dev_free(p->d_diag, st);
+    dev_free(p->d_q64, st);
   }
-  cudaFree(p->d_best_rel);
-  cudaFree(p->d_energy);
-  cudaFree(p->d_states);
-  cudaFree(p->d_xbest_ws);
-  cudaFree(p->d_tscale);
-  cudaFree(p->d_counters);
-  cudaFree(p->d_arg_idx);
-  cudaFree(p->d_arg_e);
+  dev_free(p->d_best_rel, st);
+  dev_free(p->d_energy, st);
+  dev_free(p->d_states, st);
+  dev_free(p->d_xbest_ws, st);
+  dev_free(p->d_tscale, st);
+  dev_free(p->d_counters, st);
+  dev_free(p->d_arg_idx, st);
+  dev_free(p->d_arg_e, st);
+  if (st) cudaStreamSynchronize(st);
   for (auto &e : p->ev)
     if (e) cudaEventDestroy(e);
   if (p->stream) cudaStreamDestroy(p->stream);
