@@ -66,6 +66,22 @@ __device__ __forceinline__ uint32_t smem_addr(const void *p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
 
+// NCH cp.async copies of 16 bytes: shared address + c*SSTEP  <-  global address + c*GSTEP, with
+// the offsets as immediates of the instruction.
+template <int NCH, int SSTEP, int GSTEP, int C = 0>
+struct CopyPieces {
+  static __device__ __forceinline__ void issue(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0+%2], [%1+%3], 16;" ::"r"(dst), "l"(src),
+                 "n"(C * SSTEP), "n"(C * GSTEP)
+                 : "memory");
+    CopyPieces<NCH, SSTEP, GSTEP, C + 1>::issue(dst, src);
+  }
+};
+template <int NCH, int SSTEP, int GSTEP>
+struct CopyPieces<NCH, SSTEP, GSTEP, NCH> {
+  static __device__ __forceinline__ void issue(uint32_t, const void *) {}
+};
+
 // P2: stream the rows of block i0 whose site was accepted by at least one trajectory
 // and apply them.  am[r] bit s: trajectory r flipped site i0+s; sm[r] bit s: the spin
 // was 1 before the flip (sign -1).
@@ -91,7 +107,7 @@ __device__ __forceinline__ uint32_t apply_rows(const T *__restrict__ qoff, unsig
   using C = Cfg<T, NCH, R, TH>;
   using VecT = typename C::VecT;
   constexpr int V = C::V, CHW = C::CHW;
-  constexpr int ROW_VECS = NCH * TH;  // 16-byte pieces per row
+  constexpr int ROW_BYTES = NCH * TH * 16;  // one ring slot
   static_assert(R % G == 0, "R must be a multiple of the group size");
 
   uint32_t any = 0;
@@ -112,24 +128,27 @@ __device__ __forceinline__ uint32_t apply_rows(const T *__restrict__ qoff, unsig
     for (int k = 0; k < G; ++k) grp[g] |= am[g * G + k];
   }
 
-  const T *base = qoff + (size_t)i0 * ld + (size_t)tid * V;
-  VecT *mine = reinterpret_cast<VecT *>(ring) + tid;  // slot s, piece c: mine[s*ROW_VECS + c*TH]
-  const uint32_t mine_s = smem_addr(mine);
+  // addresses: one 64-bit base per block, a 32-bit row offset per row, immediates per piece;
+  // the ring is walked with wrapping byte addresses (no per-row multiplications)
+  const unsigned char *base =
+      reinterpret_cast<const unsigned char *>(qoff + (size_t)i0 * ld + (size_t)tid * V);
+  const uint32_t row_bytes = (uint32_t)(ld * sizeof(T));
+  const unsigned char *r_lo = ring + (size_t)tid * 16;
+  const unsigned char *r_hi = r_lo + (size_t)K * ROW_BYTES;
+  const unsigned char *r_ptr = r_lo;
+  const uint32_t w_lo = smem_addr(r_lo);
+  const uint32_t w_hi = w_lo + (uint32_t)K * ROW_BYTES;
+  uint32_t w_addr = w_lo;
   uint32_t rem_issue = any, rem_apply = any;
-  int slot_w = 0, slot_r = 0;
 
   auto issue_next = [&]() {
     if (rem_issue) {
       const int s = __ffs(rem_issue) - 1;
       rem_issue &= rem_issue - 1;
-      const T *rp = base + (size_t)s * ld;
-      const uint32_t dst = mine_s + (uint32_t)slot_w * (ROW_VECS * 16);
-#pragma unroll
-      for (int c = 0; c < NCH; ++c)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + c * (TH * 16)),
-                     "l"(rp + c * CHW)
-                     : "memory");
-      slot_w = (slot_w + 1 == K) ? 0 : slot_w + 1;
+      const unsigned char *rp = base + (uint32_t)s * row_bytes;
+      CopyPieces<NCH, TH * 16, CHW * (int)sizeof(T)>::issue(w_addr, rp);
+      w_addr += ROW_BYTES;
+      if (w_addr == w_hi) w_addr = w_lo;
     }
     asm volatile("cp.async.commit_group;" ::: "memory");  // one group per step, empty or not
   };
@@ -138,15 +157,20 @@ __device__ __forceinline__ uint32_t apply_rows(const T *__restrict__ qoff, unsig
   for (int k = 0; k < K - 1; ++k) issue_next();
 #pragma unroll 1
   while (rem_apply) {
+    // row i has landed when at most K-2 younger groups are pending; read it into registers
+    // first, so that the latency of the shared-memory loads hides behind the address
+    // arithmetic of the next copies
+    asm volatile("cp.async.wait_group %0;" ::"n"(K - 2) : "memory");
+    T qv[NCH * V];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+      vec_unpack<T>(*reinterpret_cast<const VecT *>(r_ptr + c * (TH * 16)), &qv[c * V]);
+    r_ptr += ROW_BYTES;
+    if (r_ptr == r_hi) r_ptr = r_lo;
     issue_next();
-    asm volatile("cp.async.wait_group %0;" ::"n"(K - 1) : "memory");
     const int s = __ffs(rem_apply) - 1;
     rem_apply &= rem_apply - 1;
     const uint32_t bit = 1u << s;
-    T qv[NCH * V];
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) vec_unpack<T>(mine[slot_r * ROW_VECS + c * TH], &qv[c * V]);
-    slot_r = (slot_r + 1 == K) ? 0 : slot_r + 1;
     if (DBG == 1) {  // timing experiment: touch the data, skip the arithmetic
       T acc = (T)0;
 #pragma unroll

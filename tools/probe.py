@@ -52,10 +52,10 @@ def run_dense(n, prec, tries, sweeps, lo, hi, label):
 
 if "dense" in what:
     s = np.sqrt(4096)
-    run_dense(4096, capi.SWEEP_F32, 148 * 8, 4, 0.3 * s, 0.02 * s, "dense4096_f32_1wave_hot2cold")
-    run_dense(4096, capi.SWEEP_F32, 148 * 8 * 4, 4, 0.3 * s, 0.02 * s, "dense4096_f32_4waves")
-    run_dense(4096, capi.SWEEP_F32, 148 * 8, 4, 0.01 * s, 0.002 * s, "dense4096_f32_cold")
-    run_dense(4096, capi.SWEEP_F32, 148 * 8, 4, 2 * s, 1 * s, "dense4096_f32_hot")
+    run_dense(4096, capi.SWEEP_F32, 148 * 12, 4, 0.3 * s, 0.02 * s, "dense4096_f32_1wave_hot2cold")
+    run_dense(4096, capi.SWEEP_F32, 148 * 12 * 4, 4, 0.3 * s, 0.02 * s, "dense4096_f32_4waves")
+    run_dense(4096, capi.SWEEP_F32, 148 * 12, 4, 0.01 * s, 0.002 * s, "dense4096_f32_cold")
+    run_dense(4096, capi.SWEEP_F32, 148 * 12, 4, 2 * s, 1 * s, "dense4096_f32_hot")
     s = np.sqrt(1024)
     run_dense(1024, capi.SWEEP_F64, 148 * 16, 8, 0.3 * s, 0.02 * s, "dense1024_f64")
     run_dense(1024, capi.SWEEP_F32, 148 * 16, 8, 0.3 * s, 0.02 * s, "dense1024_f32")
