@@ -1,0 +1,178 @@
+"""Benchmark-harness row: Ising->QUBO converter, one-solver-sweep, distance table.
+
+Reference: benchmarks/annealing/Snakefile (grid, CSV columns), scripts/convert_qbsolv_to_coo.py,
+plot.py.  Fixtures under tests/golden/chimera{128,512} are copies of the reference's instance
+files and of rows its CLI produced (tests/golden/make_golden.py)."""
+import csv
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+BIN = os.path.join(ROOT, "build", "bin")
+sys.path.insert(0, os.path.join(ROOT, "benchmarks", "annealing"))
+
+import convert_ising_to_qubo as conv  # noqa: E402
+import distance_from_ground as dist   # noqa: E402
+
+
+def run(cmd, **kw):
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=600, **kw)
+
+
+@pytest.fixture(scope="module")
+def binaries():
+    r = run(["make", "-C", os.path.join(ROOT, "app")])
+    assert r.returncode == 0, r.stderr[-2000:]
+    return BIN
+
+
+@pytest.mark.parametrize("size", ["128", "512"])
+def test_converter_reproduces_the_reference_files(size, tmp_path):
+    """The reference ships both the Ising originals and the files its dimod-based script made
+    from them; ours must be identical byte for byte (header, term order, float text)."""
+    d = os.path.join(HERE, "golden", f"chimera{size}")
+    out = tmp_path / "out.qubo"
+    r = run([sys.executable, os.path.join(ROOT, "benchmarks", "annealing", "convert_ising_to_qubo.py"),
+             os.path.join(d, "001.ising.txt"), str(out)])
+    assert r.returncode == 0, r.stderr
+    assert out.read_text() == open(os.path.join(d, "001.qubo")).read()
+
+
+def test_converter_energy_identity():
+    """E_ising(s) = E_qubo(x) + offset for x = (s + 1) / 2 on random assignments."""
+    import random
+    rng = random.Random(5)
+    d = os.path.join(HERE, "golden", "chimera128")
+    h, coupling = conv.read_ising(open(os.path.join(d, "001.ising.txt")).read())
+    n, linear, quadratic, offset = conv.ising_to_qubo(h, coupling)
+    assert n == 128
+    for _ in range(20):
+        s = [rng.choice((-1, 1)) for _ in range(n)]
+        x = [(v + 1) // 2 for v in s]
+        assert abs(conv.ising_energy(h, coupling, s)
+                   - (dist.qubo_energy(linear, quadratic, x) + offset)) < 1e-9
+
+
+def test_sweep_rows_equal_the_per_point_cli_runs(binaries, tmp_path):
+    """One process walking the grid writes, per point, exactly the two CSV lines that
+    one-solver-anneal writes for the same parameters plus the four Snakefile columns."""
+    table = tmp_path / "table.csv"
+    qubo = os.path.join(ROOT, "examples", "csp7.qubo")
+    r = run([os.path.join(binaries, "one-solver-sweep"), "--input", qubo, "--output", str(table),
+             "--beta-min", "0.1,0.5", "--beta-max", "2", "--num-iter", "20:60:20",
+             "--num-tries", "5,25", "--schedule-type", "linear,geometric", "--device-type", "cpu"])
+    assert r.returncode == 0, r.stderr
+    rows = list(csv.reader(open(table)))
+    header, rows = rows[0], rows[1:]
+    n = len(header) - 5
+    assert header[:n] == [str(i) for i in range(n)]
+    assert header[n:] == ["energy", "beta_min", "num_iter", "num_tries", "schedule"]
+    assert len(rows) == 2 * 2 * 2 * 2
+    # order of the Snakefile's expand(): beta_min, num_iter, num_tries, schedule (innermost)
+    assert [r[n + 1:] for r in rows[:5]] == [["0.1", "20", "5", "linear"], ["0.1", "20", "5", "geometric"],
+                                             ["0.1", "20", "25", "linear"], ["0.1", "20", "25", "geometric"],
+                                             ["0.1", "40", "5", "linear"]]
+    for row in (rows[0], rows[7], rows[10], rows[15]):
+        one = tmp_path / "one.csv"
+        r = run([os.path.join(binaries, "one-solver-anneal"), "--input", qubo, "--output", str(one),
+                 "--beta-min", row[n + 1], "--beta-max", "2", "--num-iter", row[n + 2],
+                 "--num-tries", row[n + 3], "--schedule-type", row[n + 4], "--device-type", "cpu"])
+        assert r.returncode == 0, r.stderr
+        lines = one.read_text().splitlines()
+        assert lines[0] == ",".join(header[:n + 1])
+        assert lines[1] == ",".join(row[:n + 1])
+
+
+def test_sweep_reference_quirk_and_errors(binaries, tmp_path):
+    """--reference-quirk keeps the labels but anneals from beta_min 0.1 (Snakefile:63-70 never
+    passes --beta-min); malformed grids are refused like the CLI refuses bad schedules."""
+    qubo = os.path.join(ROOT, "examples", "csp7.qubo")
+    a, b = tmp_path / "a.csv", tmp_path / "b.csv"
+    common = ["--input", qubo, "--beta-max", "2", "--num-iter", "30", "--num-tries", "8",
+              "--schedule-type", "geometric", "--quiet"]
+    assert run([os.path.join(binaries, "one-solver-sweep"), *common, "--output", str(a),
+                "--beta-min", "0.1,0.9", "--reference-quirk"]).returncode == 0
+    assert run([os.path.join(binaries, "one-solver-sweep"), *common, "--output", str(b),
+                "--beta-min", "0.1"]).returncode == 0
+    ra, rb = list(csv.reader(open(a)))[1:], list(csv.reader(open(b)))[1:]
+    assert ra[0][:-4] == ra[1][:-4] == rb[0][:-4]       # both groups ran the beta_min 0.1 anneal
+    assert [r[-4] for r in ra] == ["0.1", "0.9"]        # ... under their own labels
+    r = run([os.path.join(binaries, "one-solver-sweep"), *common, "--output", str(a), "--beta-min", "3"])
+    assert r.returncode != 0 and "initial beta is not lesser than final beta" in r.stderr
+    r = run([os.path.join(binaries, "one-solver-sweep"), *common[:-1], "--output", str(a),
+             "--schedule-type", "cubic"])
+    assert r.returncode != 0 and "Unknown beta schedule: cubic" in r.stderr
+
+
+def _ground_file(tmp_path, size):
+    tn = json.load(open(os.path.join(HERE, "golden", f"chimera{size}", "groundstate_TN.json")))
+    path = tmp_path / "groundstates_TN.txt"
+    path.write_text(f"{tn['file']} : {tn['ising_energy']} " + " ".join(str(s) for s in tn["spins"]) + "\n")
+    return path, tn
+
+
+def test_distance_table_on_reference_results(tmp_path):
+    """Rows the reference CLI produced (results/128/001.csv) against the tensor-network ground
+    state: every distance is >= 0, and the ground energy matches the Ising value."""
+    d = os.path.join(HERE, "golden", "chimera128")
+    ground_path, tn = _ground_file(tmp_path, "128")
+    h, coupling = conv.read_ising(open(os.path.join(d, "001.ising.txt")).read())
+    _, linear, quadratic, offset = conv.ising_to_qubo(h, coupling)
+    e_ising, spins = dist.read_ground_state(str(ground_path), "001.txt")
+    assert e_ising == tn["ising_energy"] and spins == tn["spins"]
+    ground = dist.qubo_energy(linear, quadratic, [(s + 1) // 2 for s in spins])
+    assert abs(ground + offset - e_ising) < 1e-4
+    sample = json.load(open(os.path.join(d, "reference_results_sample.json")))
+    results = tmp_path / "results.csv"
+    with open(results, "w") as f:
+        n = len(sample[0]["state"])
+        f.write(",".join(str(i) for i in range(n)) + ",energy,beta_min,num_iter,num_tries,schedule\n")
+        for r in sample:
+            f.write(",".join(r["state"]) + f",{r['energy']},{r['beta_min']},{r['num_iter']},"
+                    f"{r['num_tries']},{r['schedule']}\n")
+    table = dist.distance_table(dist.read_results(str(results)), ground)
+    assert table and all(v >= -1e-6 for cell in table.values() for v in cell.values())
+    r = run([sys.executable, os.path.join(ROOT, "benchmarks", "annealing", "distance_from_ground.py"),
+             "--results", str(results), "--ising", os.path.join(d, "001.ising.txt"),
+             "--ground-states", str(ground_path)])
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.splitlines()[1].startswith("num_tries,schedule,")
+
+
+@pytest.mark.gpu
+def test_sweep_on_the_gpu_matches_cli_and_respects_the_ground_state(binaries, tmp_path):
+    """chimera128 on the B200 engine: sweep rows == per-point gpu CLI runs == cpu engine rows, and
+    no energy lies below the tensor-network ground state."""
+    d = os.path.join(HERE, "golden", "chimera128")
+    qubo = os.path.join(d, "001.qubo")
+    grid = ["--beta-min", "0.1,1.1", "--beta-max", "10", "--num-iter", "100,400",
+            "--num-tries", "60,460", "--schedule-type", "linear,geometric", "--quiet"]
+    gpu, cpu = tmp_path / "gpu.csv", tmp_path / "cpu.csv"
+    r = run([os.path.join(binaries, "one-solver-sweep"), "--input", qubo, "--output", str(gpu),
+             "--device-type", "gpu", *grid])
+    assert r.returncode == 0, r.stderr
+    r = run([os.path.join(binaries, "one-solver-sweep"), "--input", qubo, "--output", str(cpu),
+             "--device-type", "cpu", *grid])
+    assert r.returncode == 0, r.stderr
+    assert gpu.read_text() == cpu.read_text()
+    rows = list(csv.reader(open(gpu)))[1:]
+    assert len(rows) == 16
+    row = rows[13]
+    one = tmp_path / "one.csv"
+    r = run([os.path.join(binaries, "one-solver-anneal"), "--input", qubo, "--output", str(one),
+             "--beta-min", row[-4], "--beta-max", "10", "--num-iter", row[-3], "--num-tries", row[-2],
+             "--schedule-type", row[-1], "--device-type", "gpu"])
+    assert r.returncode == 0, r.stderr
+    assert one.read_text().splitlines()[1] == ",".join(row[:-4])
+    ground_path, _ = _ground_file(tmp_path, "128")
+    h, coupling = conv.read_ising(open(os.path.join(d, "001.ising.txt")).read())
+    _, linear, quadratic, _ = conv.ising_to_qubo(h, coupling)
+    _, spins = dist.read_ground_state(str(ground_path), "001.txt")
+    ground = dist.qubo_energy(linear, quadratic, [(s + 1) // 2 for s in spins])
+    table = dist.distance_table(dist.read_results(str(gpu)), ground)
+    assert all(v >= -1e-4 for cell in table.values() for v in cell.values())
