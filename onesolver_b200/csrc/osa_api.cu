@@ -64,7 +64,7 @@ struct osa_problem {
   void *d_qoff = nullptr; // zero-diagonal symmetric copy, sweep precision
   void *d_diag = nullptr; // [ld] sweep precision
   size_t ld64 = 0;
-  double *d_q64 = nullptr; // [n][ld64] original values incl. diagonal (exact energies)
+  double *d_q64 = nullptr; // [rows_pad][ld64] original values incl. diagonal (exact energies)
   // csr
   int64_t nnz = 0;
   int32_t *d_rowptr = nullptr, *d_col = nullptr;
@@ -201,7 +201,7 @@ int create_dense(const TIn *qsym, int n, int device, int prec, osa_problem **out
   const size_t esz = prec == OSA_SWEEP_F32 ? 4 : 8;
   p->ld = round_up((size_t)n, prec == OSA_SWEEP_F32 ? 1024 : 512);
   p->rows_pad = round_up((size_t)n, 32);
-  p->ld64 = round_up((size_t)n, 2);
+  p->ld64 = round_up((size_t)n, 32);  // zero padded: the MMA energy kernel reads whole 32x32 tiles
 
   TIn *d_in = nullptr;
   int *d_bad = nullptr;
@@ -222,12 +222,12 @@ int create_dense(const TIn *qsym, int n, int device, int prec, osa_problem **out
   TRY_B(dev_alloc(&d_bad, sizeof(int), p->stream));
   TRY_B(dev_alloc(&p->d_qoff, p->rows_pad * p->ld * esz, p->stream));
   TRY_B(dev_alloc(&p->d_diag, p->ld * esz, p->stream));
-  TRY_B(dev_alloc(&p->d_q64, (size_t)n * p->ld64 * sizeof(double), p->stream));
+  TRY_B(dev_alloc(&p->d_q64, p->rows_pad * p->ld64 * sizeof(double), p->stream));
   TRY_B(cudaMemcpyAsync(d_in, qsym, total * sizeof(TIn), cudaMemcpyHostToDevice, p->stream));
   TRY_B(cudaMemsetAsync(d_bad, 0, sizeof(int), p->stream));
   TRY_B(cudaMemsetAsync(p->d_qoff, 0, p->rows_pad * p->ld * esz, p->stream));
   TRY_B(cudaMemsetAsync(p->d_diag, 0, p->ld * esz, p->stream));
-  TRY_B(cudaMemsetAsync(p->d_q64, 0, (size_t)n * p->ld64 * sizeof(double), p->stream));
+  TRY_B(cudaMemsetAsync(p->d_q64, 0, p->rows_pad * p->ld64 * sizeof(double), p->stream));
   const int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
   k_check_symmetric<TIn><<<grid, 256, 0, p->stream>>>(d_in, n, d_bad);
   if (prec == OSA_SWEEP_F32)

@@ -5,6 +5,8 @@
 //   E(x) = sum_{i<=j} Q[i][j] x_i x_j   (upper triangle incl. diagonal, fp64)
 // for a batch of bit-packed states.  K4 is the host epilogue std::min_element
 // (annealing.hpp:134-135): first minimum wins ties.
+#include <cstdlib>
+
 #include "osa_common.cuh"
 
 namespace osa {
@@ -78,6 +80,106 @@ __global__ void __launch_bounds__(256) k_energy_dense(const double *__restrict__
     for (int w = 0; w < 8; ++w) v += s_red[w][lane];
     const uint64_t t = batch0 + lane;
     if (t < count) out[t] = v;
+  }
+}
+
+// Dense, tensor-core version: E_r = sum_j x_rj * Y_rj with Y = X * Qu, Qu the upper triangle
+// incl. the diagonal -- the one dense contraction of the annealing path -- on the FP64 tensor
+// cores (mma.sync m8n8k4, DMMA).  A warp scores 32 states (four 8-row A tiles) against 32 columns
+// at a time (four 8-column B tiles, 16 accumulator tiles in registers) and walks k = row index of
+// Q only up to the diagonal block; entries below the diagonal are zeroed in the B fragment.  The
+// A fragments are the spins themselves (bit -> 0.0 / 1.0), read from the packed states through
+// L1; all warps of a CTA walk the same Q tiles, so Q reaches the SM once per CTA (256 states).
+// q64 is padded with zeros to multiples of 32 in both directions.
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+template <int W>  // warps per CTA
+__global__ void __launch_bounds__(W * 32, 16 / W) k_energy_dense_mma(
+    const double *__restrict__ q64, size_t ld64, int n, const uint32_t *__restrict__ states, int nw,
+    uint64_t count, double *__restrict__ out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gid = lane >> 2, tig = lane & 3;
+  const uint64_t t0 = ((uint64_t)blockIdx.x * (uint64_t)W + (uint64_t)warp) * 32ull;
+  if (t0 >= count) return;
+  // the four state rows this thread feeds into the A fragments: r = mt*8 + gid
+  const uint32_t *srow[4];
+  bool valid[4];
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt) {
+    const uint64_t t = t0 + (uint64_t)(mt * 8 + gid);
+    valid[mt] = t < count;
+    srow[mt] = states + (valid[mt] ? t : t0) * (uint64_t)nw;
+  }
+  double e_acc[4] = {0.0, 0.0, 0.0, 0.0};
+  const int nblk = (n + 31) >> 5;
+
+  for (int jb = 0; jb < nblk; ++jb) {
+    const int j0 = jb * 32;
+    double c[4][4][2];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) c[mt][nt][0] = c[mt][nt][1] = 0.0;
+
+    // B fragment of n-tile nt: element (k = tig, n = gid) is Q[k0 + tig][j0 + gid*4 + nt], so the
+    // four n-tiles of a thread are four consecutive doubles (two 16-byte loads); the matching
+    // C fragment (row gid, n = tig*2 + e) then belongs to column j0 + (tig*2 + e)*4 + nt.
+    const double *bp = q64 + (size_t)tig * ld64 + (size_t)(j0 + gid * 4);
+    const size_t kstride = 4 * ld64;
+    const int ksteps = (j0 + 32) >> 2;
+    const int kdiag = j0 >> 2;  // first k-step inside the diagonal block
+    double2 b01 = __ldg(reinterpret_cast<const double2 *>(bp));
+    double2 b23 = __ldg(reinterpret_cast<const double2 *>(bp) + 1);
+    uint32_t xw[4] = {0u, 0u, 0u, 0u};
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const int i = ks * 4 + tig;
+      if ((ks & 7) == 0) {
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) xw[mt] = valid[mt] ? __ldg(srow[mt] + (ks >> 3)) : 0u;
+      }
+      double2 n01 = b01, n23 = b23;
+      if (ks + 1 < ksteps) {
+        const double *np = bp + (size_t)(ks + 1) * kstride;
+        n01 = __ldg(reinterpret_cast<const double2 *>(np));
+        n23 = __ldg(reinterpret_cast<const double2 *>(np) + 1);
+      }
+      double b[4] = {b01.x, b01.y, b23.x, b23.y};
+      if (ks >= kdiag) {  // diagonal block: keep i <= j only
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+          if (i > j0 + gid * 4 + nt) b[nt] = 0.0;
+      }
+      double a[4];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) a[mt] = ((xw[mt] >> (i & 31)) & 1u) ? 1.0 : 0.0;
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dmma(c[mt][nt], a[mt], b[nt]);
+      b01 = n01;
+      b23 = n23;
+    }
+    // E_r += sum over the block's columns of x_rj * Y_rj
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+      const uint32_t w = valid[mt] ? __ldg(srow[mt] + jb) : 0u;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          if ((w >> ((tig * 2 + e) * 4 + nt)) & 1u) e_acc[mt] += c[mt][nt][e];
+    }
+  }
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt) {
+    double v = e_acc[mt];
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    if (tig == 0 && valid[mt]) out[t0 + (uint64_t)(mt * 8 + gid)] = v;
   }
 }
 
@@ -181,6 +283,23 @@ __global__ void __launch_bounds__(256) k_read_bw(const uint4 *__restrict__ buf, 
 cudaError_t launch_energy_dense(const double *q64, size_t ld64, int n, const uint32_t *states,
                                 int nw, uint64_t count, double *out, cudaStream_t s) {
   if (count == 0) return cudaSuccess;
+  static const bool use_mma = [] {  // OSA_ENERGY_MMA=0: the CUDA-core kernel (A/B measurements)
+    const char *e = getenv("OSA_ENERGY_MMA");
+    return !(e && atoi(e) == 0);
+  }();
+  if (use_mma) {
+    static const int w = [] {  // tuning knob: warps (32-state tiles) per CTA
+      const char *e = getenv("OSA_ENERGY_W");
+      return e ? atoi(e) : 1;  // measured best at N=4096 (profiles/r01/energy_mma_v16.log)
+    }();
+    const uint64_t g = (count + 32ull * w - 1) / (32ull * w);
+    if (g > 0x7fffffffull) return cudaErrorInvalidValue;
+    if (w == 8) k_energy_dense_mma<8><<<(unsigned)g, 256, 0, s>>>(q64, ld64, n, states, nw, count, out);
+    else if (w == 2) k_energy_dense_mma<2><<<(unsigned)g, 64, 0, s>>>(q64, ld64, n, states, nw, count, out);
+    else if (w == 1) k_energy_dense_mma<1><<<(unsigned)g, 32, 0, s>>>(q64, ld64, n, states, nw, count, out);
+    else k_energy_dense_mma<4><<<(unsigned)g, 128, 0, s>>>(q64, ld64, n, states, nw, count, out);
+    return cudaGetLastError();
+  }
   const size_t smem = (size_t)nw * 32 * sizeof(uint32_t);
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
   cudaError_t err =
