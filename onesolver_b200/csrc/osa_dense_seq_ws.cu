@@ -52,6 +52,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_dense_seq_ws(const DenseParam
   __shared__ __align__(16) T s_tile_x[32][32];   // rows of the previous block x columns of this one
   __shared__ uint32_t s_acc[2][R];               // accept / sign masks of block g (parity g&1)
   __shared__ uint32_t s_sign[2][R];
+  // per-trajectory walk state of the decide warps (indexed by a run-time trajectory number, so it
+  // lives here rather than in a register array that the compiler would demote to local memory)
+  __shared__ double s_erel[R], s_best[R];
+  __shared__ uint32_t s_atbest[R];
   __shared__ uint32_t s_x[R][NWP];
   __shared__ uint32_t s_xb[R][NWP];
 
@@ -175,13 +179,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_dense_seq_ws(const DenseParam
         }
       }
     }
-    double erel[TPD], best[TPD];
-    bool at_best[TPD];
-#pragma unroll
-    for (int rr = 0; rr < TPD; ++rr) {
-      erel[rr] = 0.0;
-      best[rr] = 0.0;
-      at_best[rr] = true;
+    for (int r = dt; r < R; r += WS_DECIDE_WARPS * 32) {
+      s_erel[r] = 0.0;
+      s_best[r] = 0.0;
+      s_atbest[r] = 1u;
     }
     unsigned long long cnt_acc = 0;
     long long t_decide = 0;
@@ -228,6 +229,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_dense_seq_ws(const DenseParam
           const T theta = threshold<T>(ts, pick(d, (uint32_t)site & 3u));
           const bool lane_ok = tv && site < n;
           uint32_t acc = 0, sg = 0, from = 0xffffffffu;
+          double erel = s_erel[r], best = s_best[r];
+          bool at_best = s_atbest[r] != 0u;
           for (;;) {
             const uint32_t xl = (xw >> lane) & 1u;
             const T dEl = xl ? -hl : hl;
@@ -238,18 +241,18 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_dense_seq_ws(const DenseParam
             const uint32_t xbit = (xw >> s) & 1u;
             const T sgn = xbit ? (T)-1 : (T)1;
             hl = det::fma(sgn, s_tile_d[s][lane], hl);
-            const double e = det::add(erel[rr], (double)dEs);
-            erel[rr] = e;
-            if (e < best[rr]) {
-              best[rr] = e;
-              at_best[rr] = true;
-            } else if (at_best[rr]) {
+            const double e = det::add(erel, (double)dEs);
+            erel = e;
+            if (e < best) {
+              best = e;
+              at_best = true;
+            } else if (at_best) {
               // leaving the best state: snapshot the state as it was BEFORE this flip
               for (int k = lane; k < nblk; k += 32) s_xb[r][k] = s_x[r][k];
               __syncwarp();
               if (lane == 0) s_xb[r][b] = xw;
               __syncwarp();
-              at_best[rr] = false;
+              at_best = false;
             }
             xw ^= (1u << s);
             acc |= (1u << s);
@@ -257,6 +260,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_dense_seq_ws(const DenseParam
             from = (s == 31) ? 0u : (0xffffffffu << (s + 1));
           }
           if (lane == 0) {
+            s_erel[r] = erel;
+            s_best[r] = best;
+            s_atbest[r] = at_best ? 1u : 0u;
             s_x[r][b] = xw;
             s_acc[par][r] = acc;
             s_sign[par][r] = sg;
@@ -286,13 +292,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_dense_seq_ws(const DenseParam
     for (int rr = 0; rr < TPD; ++rr) {
       const int r = dwarp + rr * WS_DECIDE_WARPS;
       if (r < R && r < nvalid) {
-        if (at_best[rr]) {
+        if (s_atbest[r]) {
           for (int k = lane; k < nblk; k += 32) s_xb[r][k] = s_x[r][k];
         }
         __syncwarp();
         const uint64_t tl = batch0 + (uint64_t)r;
         for (int k = lane; k < p.nw; k += 32) p.best_states[tl * (uint64_t)p.nw + k] = s_xb[r][k];
-        if (lane == 0) p.best_rel[tl] = best[rr];
+        if (lane == 0) p.best_rel[tl] = s_best[r];
       }
     }
     if (lane == 0) {

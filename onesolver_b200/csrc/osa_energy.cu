@@ -85,26 +85,29 @@ __global__ void __launch_bounds__(256) k_energy_dense(const double *__restrict__
 
 // Dense, tensor-core version: E_r = sum_j x_rj * Y_rj with Y = X * Qu, Qu the upper triangle
 // incl. the diagonal -- the one dense contraction of the annealing path -- on the FP64 tensor
-// cores (mma.sync m8n8k4, DMMA).  A warp scores 32 states (four 8-row A tiles) against 32 columns
-// at a time (four 8-column B tiles, 16 accumulator tiles in registers) and walks k = row index of
-// Q only up to the diagonal block; entries below the diagonal are zeroed in the B fragment.  The
-// A fragments are the spins themselves (bit -> 0.0 / 1.0), read from the packed states through
-// L1; all warps of a CTA walk the same Q tiles, so Q reaches the SM once per CTA (256 states).
-// q64 is padded with zeros to multiples of 32 in both directions.
+// cores (mma.sync m8n8k4, DMMA).  A CTA scores 32 states; each of its 8 warps takes every 8th
+// block of 32 columns (in a zig-zag, so the triangular work is balanced), holds the 32x32 block of
+// Y as 16 accumulator tiles in registers (four 8-row A tiles x four 8-column B tiles) and walks
+// k = row index of Q only up to the diagonal block; entries below the diagonal are zeroed in the
+// B fragment.  The A fragments are the spins themselves (bit -> 0.0 / 1.0), read from the packed
+// states through L1.  The eight partial sums are added in warp order, so a state's energy does not
+// depend on how many other states are scored with it.  q64 is padded with zeros to multiples of
+// 32 in both directions.
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c[0]), "+d"(c[1])
                : "d"(a), "d"(b));
 }
 
-template <int W>  // warps per CTA
-__global__ void __launch_bounds__(W * 32, 16 / W) k_energy_dense_mma(
+constexpr int EMMA_WARPS = 8;
+
+__global__ void __launch_bounds__(EMMA_WARPS * 32, 2) k_energy_dense_mma(
     const double *__restrict__ q64, size_t ld64, int n, const uint32_t *__restrict__ states, int nw,
     uint64_t count, double *__restrict__ out) {
+  __shared__ double s_part[EMMA_WARPS][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gid = lane >> 2, tig = lane & 3;
-  const uint64_t t0 = ((uint64_t)blockIdx.x * (uint64_t)W + (uint64_t)warp) * 32ull;
-  if (t0 >= count) return;
+  const uint64_t t0 = (uint64_t)blockIdx.x * 32ull;
   // the four state rows this thread feeds into the A fragments: r = mt*8 + gid
   const uint32_t *srow[4];
   bool valid[4];
@@ -117,7 +120,11 @@ __global__ void __launch_bounds__(W * 32, 16 / W) k_energy_dense_mma(
   double e_acc[4] = {0.0, 0.0, 0.0, 0.0};
   const int nblk = (n + 31) >> 5;
 
-  for (int jb = 0; jb < nblk; ++jb) {
+  // column blocks of this warp: 16m + warp and 16m + 15 - warp, m = 0, 1, ...
+  for (int jq = 0;; ++jq) {
+    const int jb = (jq >> 1) * (2 * EMMA_WARPS) + ((jq & 1) ? (2 * EMMA_WARPS - 1 - warp) : warp);
+    if ((jq >> 1) * (2 * EMMA_WARPS) >= nblk) break;
+    if (jb >= nblk) continue;
     const int j0 = jb * 32;
     double c[4][4][2];
 #pragma unroll
@@ -179,7 +186,14 @@ __global__ void __launch_bounds__(W * 32, 16 / W) k_energy_dense_mma(
     double v = e_acc[mt];
     v += __shfl_xor_sync(0xffffffffu, v, 1);
     v += __shfl_xor_sync(0xffffffffu, v, 2);
-    if (tig == 0 && valid[mt]) out[t0 + (uint64_t)(mt * 8 + gid)] = v;
+    if (tig == 0) s_part[warp][mt * 8 + gid] = v;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < EMMA_WARPS; ++w) v += s_part[w][lane];
+    if (t0 + (uint64_t)lane < count) out[t0 + (uint64_t)lane] = v;
   }
 }
 
@@ -288,16 +302,9 @@ cudaError_t launch_energy_dense(const double *q64, size_t ld64, int n, const uin
     return !(e && atoi(e) == 0);
   }();
   if (use_mma) {
-    static const int w = [] {  // tuning knob: warps (32-state tiles) per CTA
-      const char *e = getenv("OSA_ENERGY_W");
-      return e ? atoi(e) : 1;  // measured best at N=4096 (profiles/r01/energy_mma_v16.log)
-    }();
-    const uint64_t g = (count + 32ull * w - 1) / (32ull * w);
+    const uint64_t g = (count + 31) / 32;
     if (g > 0x7fffffffull) return cudaErrorInvalidValue;
-    if (w == 8) k_energy_dense_mma<8><<<(unsigned)g, 256, 0, s>>>(q64, ld64, n, states, nw, count, out);
-    else if (w == 2) k_energy_dense_mma<2><<<(unsigned)g, 64, 0, s>>>(q64, ld64, n, states, nw, count, out);
-    else if (w == 1) k_energy_dense_mma<1><<<(unsigned)g, 32, 0, s>>>(q64, ld64, n, states, nw, count, out);
-    else k_energy_dense_mma<4><<<(unsigned)g, 128, 0, s>>>(q64, ld64, n, states, nw, count, out);
+    k_energy_dense_mma<<<(unsigned)g, EMMA_WARPS * 32, 0, s>>>(q64, ld64, n, states, nw, count, out);
     return cudaGetLastError();
   }
   const size_t smem = (size_t)nw * 32 * sizeof(uint32_t);
