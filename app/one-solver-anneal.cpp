@@ -7,7 +7,10 @@
 // --device-type (host); exit 0 on success/help, -1 on bad arguments or an unreadable input,
 // 1 on an exception.  Extra flags (all optional, defaults keep the reference behaviour):
 // --mode random|sweep, --accept reference|boltzmann, --sweeps-per-beta, --seed,
-// --precision f64|f32, --layout auto|dense|csr, --gpu-index, --stats.
+// --precision f64|f32, --layout auto|dense|csr, --gpu-index, --stats; --algorithm sa|pt with
+// --num-replicas: parallel tempering (GPU only) -- the beta range becomes a ladder of
+// --num-replicas temperatures (built by the chosen schedule type), --num-iter counts rounds,
+// --sweeps-per-beta the sweeps per round and --num-tries the independent ladders.
 #include <fstream>
 #include <iostream>
 #include <memory>
@@ -39,7 +42,9 @@ int main(int argc, char *argv[]) {
         .add("precision", true, "f64", "sweep arithmetic on the gpu: f64 or f32")
         .add("layout", true, "auto", "gpu problem layout: auto, dense or csr")
         .add("gpu-index", true, "0", "CUDA device to use with --device-type gpu")
-        .add("stats", false, "", "print engine statistics (gpu)");
+        .add("stats", false, "", "print engine statistics (gpu)")
+        .add("algorithm", true, "sa", "sa (simulated annealing) or pt (parallel tempering, gpu)")
+        .add("num-replicas", true, "12", "temperatures per ladder with --algorithm pt");
     options.parse(argc, argv);
 
     if (options.count("help")) {
@@ -96,6 +101,16 @@ int main(int argc, char *argv[]) {
       std::cerr << "Unknown layout: " << layout << std::endl;
       return -1;
     }
+    const std::string algorithm = options.str("algorithm");
+    if (algorithm != "sa" && algorithm != "pt") {
+      std::cerr << "Unknown algorithm: " << algorithm << std::endl;
+      return -1;
+    }
+    const unsigned int num_replicas = static_cast<unsigned int>(options.uint("num-replicas"));
+    if (algorithm == "pt" && num_replicas < 2) {
+      std::cerr << "Parallel tempering needs at least two replicas" << std::endl;
+      return -1;
+    }
     engine.mode = mode == "sweep" ? OSA_MODE_SEQUENTIAL_SWEEP : OSA_MODE_RANDOM_SITE;
     engine.accept_rule = accept == "boltzmann" ? OSA_ACCEPT_BOLTZMANN : OSA_ACCEPT_REFERENCE;
     engine.sweep_precision = precision == "f32" ? OSA_SWEEP_F32 : OSA_SWEEP_F64;
@@ -132,15 +147,21 @@ int main(int argc, char *argv[]) {
     }
     std::cout << "Using device: " << q_ptr->device_name() << std::endl;
 
-    std::vector<double> beta_schedule(num_iter);
+    // simulated annealing: one beta per iteration; parallel tempering: one beta per replica
+    const unsigned int ladder = algorithm == "pt" ? num_replicas : num_iter;
+    std::vector<double> beta_schedule(ladder);
     if (schedule_type == "linear") {
-      construct_linear_beta_schedule(beta_schedule, beta_min, beta_max, num_iter);
+      construct_linear_beta_schedule(beta_schedule, beta_min, beta_max, ladder);
     } else {
-      construct_geometric_beta_schedule(beta_schedule, beta_min, beta_max, num_iter);
+      construct_geometric_beta_schedule(beta_schedule, beta_min, beta_max, ladder);
     }
 
-    auto solution = sa::anneal(instance, *q_ptr, beta_schedule, static_cast<int>(num_iter),
-                               num_tries, sweeps_per_beta, engine);
+    auto solution =
+        algorithm == "pt"
+            ? sa::parallel_tempering(instance, *q_ptr, beta_schedule, static_cast<int>(num_iter),
+                                     sweeps_per_beta, num_tries, engine)
+            : sa::anneal(instance, *q_ptr, beta_schedule, static_cast<int>(num_iter), num_tries,
+                         sweeps_per_beta, engine);
 
     std::ofstream results_file(output_file);
     solution.save(results_file);
@@ -151,6 +172,7 @@ int main(int argc, char *argv[]) {
                 << ", accepts " << stats.accepts << ", row fetches " << stats.row_fetches
                 << ", device ms " << stats.ms_total << " (sweep " << stats.ms_sweep << ", energy "
                 << stats.ms_energy << ")" << std::endl;
+      if (algorithm == "pt") std::cout << "Replica exchanges accepted: " << stats.pt_swaps << std::endl;
     }
   } catch (std::exception &e) {
     std::cerr << "error: " << e.what() << "\n";

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define OSA_ABI_VERSION 1
+#define OSA_ABI_VERSION 2
 
 typedef enum {
   OSA_OK = 0,
@@ -87,6 +87,7 @@ typedef struct {
   int32_t reserved;
   /* diagnostics of the dense sequential kernel: SM cycles summed over CTAs (0 elsewhere) */
   uint64_t cyc_decide, cyc_apply, cyc_stage, cyc_init;
+  uint64_t pt_swaps;         /* osa_pt_anneal: accepted replica exchanges */
 } osa_stats;
 
 /* ---- library / device ---------------------------------------------------- */
@@ -124,6 +125,31 @@ int osa_problem_size(const osa_problem *p, int *n, int *is_sparse, int *sweep_pr
 int osa_anneal(osa_problem *p, const double *beta_schedule, const osa_anneal_params *params,
                double *best_energies, uint32_t *best_states_packed, uint8_t *best_state,
                double *best_energy, uint64_t *best_index, osa_stats *stats);
+
+/* ---- parallel tempering on top of the same sweep kernel.  The reference has no such sampler; its
+ *      benchmark report recommends one (benchmarks/annealing/performance.md:54-59).
+ * num_groups independent runs of num_replicas replicas each; betas[num_replicas] is the ladder
+ * (strictly increasing, positive).  Per round every replica does sweeps_per_round sequential
+ * sweeps at its current beta, then neighbouring rungs (even pairs in even rounds, odd pairs in odd
+ * rounds) exchange configurations with the Metropolis probability computed from exact fp64
+ * energies.  Trajectory id = first_group * num_replicas + group * num_replicas + slot; slot k
+ * starts on rung k.  Dense problems with n <= 8192 (fp32 sweeps) / 4096 (fp64 sweeps) only.
+ * Outputs as in osa_anneal, per trajectory (= per replica slot): the best state each one visited. */
+typedef struct osa_pt_params {
+  uint64_t seed;             /* 1234 like annealing.hpp:87 */
+  uint64_t first_group;      /* id offset when a run is sharded over GPUs */
+  uint64_t num_groups;
+  int32_t num_replicas;
+  int32_t num_rounds;
+  int32_t sweeps_per_round;
+  int32_t accept_rule;       /* OSA_ACCEPT_*: also selects the Boltzmann weight of the exchange */
+  uint32_t flags;            /* must be 0 */
+  int32_t reserved;
+} osa_pt_params;
+
+int osa_pt_anneal(osa_problem *p, const double *betas, const osa_pt_params *params,
+                  double *best_energies, uint32_t *best_states_packed, uint8_t *best_state,
+                  double *best_energy, uint64_t *best_index, osa_stats *stats);
 
 /* sa::energy (annealing.hpp:31-40) for a batch of packed states, fp64 on the device */
 int osa_energy_batch(osa_problem *p, const uint32_t *states_packed, uint64_t count, double *out);

@@ -162,6 +162,44 @@ qubo::Solution anneal(qubo::QUBOModel<int, T> instance, devices::queue q,
   return qubo::Solution(bits.begin(), bits.end(), energies[best_idx]);
 }
 
+// Parallel tempering on the GPU engine (osa_pt_anneal).  The reference has no such sampler; its
+// benchmark report names it as the next step (benchmarks/annealing/performance.md:54-59).
+// `betas` is the temperature ladder (strictly increasing); num_groups independent ladders are run
+// for num_rounds rounds of sweeps_per_round sequential sweeps, with a replica-exchange step after
+// every round.  opt.accept_rule selects the Boltzmann weight (exp(-beta E) or, with the
+// reference's rule, exp(-E / beta)); opt.first_try is the id of the first GROUP.  GPU only.
+template <typename T>
+qubo::Solution parallel_tempering(qubo::QUBOModel<int, T> instance, devices::queue q,
+                                  const std::vector<double> &betas, int num_rounds,
+                                  int sweeps_per_round, unsigned int num_groups,
+                                  const Options &opt = Options()) {
+  const int N = static_cast<int>(instance.get_nodes());
+  if (N <= 0) throw std::invalid_argument("parallel_tempering: the model has no variables");
+  if (!q.is_gpu())
+    throw std::runtime_error("parallel_tempering: only --device-type gpu runs parallel tempering");
+  detail::ProblemGuard guard;
+  const auto flat = helpers::flatten_qubo(instance);
+  std::vector<double> flat64(flat.begin(), flat.end());
+  detail::check(osa_problem_create_dense_f64(flat64.data(), N, q.cuda_device(), opt.sweep_precision,
+                                             &guard.p),
+                "osa_problem_create_dense_f64");
+  osa_pt_params prm{};
+  prm.seed = opt.seed;
+  prm.first_group = opt.first_try;
+  prm.num_groups = num_groups;
+  prm.num_replicas = static_cast<std::int32_t>(betas.size());
+  prm.num_rounds = num_rounds;
+  prm.sweeps_per_round = sweeps_per_round;
+  prm.accept_rule = opt.accept_rule;
+  std::vector<std::uint8_t> state(N);
+  double best_energy = 0.0;
+  std::uint64_t best_index = 0;
+  detail::check(osa_pt_anneal(guard.p, betas.data(), &prm, nullptr, nullptr, state.data(),
+                              &best_energy, &best_index, opt.stats),
+                "osa_pt_anneal");
+  return qubo::Solution(state.begin(), state.end(), best_energy);
+}
+
 }  // namespace sa
 
 #endif

@@ -118,6 +118,31 @@ class Problem:
                                   ctypes.byref(st)))
         return AnnealResult(state, e.value, idx.value, st.as_dict(), energies, states)
 
+    def parallel_tempering(self, betas, num_groups, num_rounds, sweeps_per_round, seed=1234,
+                           first_group=0, accept_rule=capi.ACCEPT_BOLTZMANN, want_energies=False,
+                           want_states=False):
+        """osa_pt_anneal: num_groups independent ladders of len(betas) replicas (see the header)."""
+        lib = capi.load()
+        ladder = np.ascontiguousarray(betas, dtype=np.float64)
+        m = int(ladder.shape[0])
+        tries = int(num_groups) * m
+        prm = capi.PtParams(seed=seed, first_group=first_group, num_groups=num_groups,
+                            num_replicas=m, num_rounds=num_rounds,
+                            sweeps_per_round=sweeps_per_round, accept_rule=accept_rule, flags=0,
+                            reserved=0)
+        energies = np.empty(tries, dtype=np.float64) if want_energies else None
+        states = np.empty((tries, self.nw), dtype=np.uint32) if want_states else None
+        state = np.empty(self.n, dtype=np.uint8)
+        e = ctypes.c_double()
+        idx = ctypes.c_uint64()
+        st = capi.Stats()
+        capi.check(lib.osa_pt_anneal(self._h, ladder.ctypes.data, ctypes.byref(prm),
+                                     energies.ctypes.data if want_energies else None,
+                                     states.ctypes.data if want_states else None,
+                                     state.ctypes.data, ctypes.byref(e), ctypes.byref(idx),
+                                     ctypes.byref(st)))
+        return AnnealResult(state, e.value, idx.value, st.as_dict(), energies, states)
+
     def energy_batch(self, states_packed):
         """sa::energy (annealing.hpp:31-40) of packed states, evaluated on the device."""
         lib = capi.load()

@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "osa_abi_version", "osa_last_error", "osa_device_count", "osa_device_name",
     "osa_kernel_name", "osa_problem_create_dense_f64", "osa_problem_create_dense_f32",
     "osa_problem_create_csr_f64", "osa_problem_destroy", "osa_problem_size", "osa_anneal",
-    "osa_energy_batch", "osa_exhaustive_dense_f64", "osa_host_alloc_pinned",
+    "osa_pt_anneal", "osa_energy_batch", "osa_exhaustive_dense_f64", "osa_host_alloc_pinned",
     "osa_host_free_pinned", "osa_measure_read_bandwidth",
 ]
 
@@ -37,6 +37,20 @@ class AnnealParams(ctypes.Structure):
         ("accept_rule", ctypes.c_int32),
         ("kernel_variant", ctypes.c_int32),
         ("flags", ctypes.c_int32),
+    ]
+
+
+class PtParams(ctypes.Structure):
+    _fields_ = [
+        ("seed", ctypes.c_uint64),
+        ("first_group", ctypes.c_uint64),
+        ("num_groups", ctypes.c_uint64),
+        ("num_replicas", ctypes.c_int32),
+        ("num_rounds", ctypes.c_int32),
+        ("sweeps_per_round", ctypes.c_int32),
+        ("accept_rule", ctypes.c_int32),
+        ("flags", ctypes.c_uint32),
+        ("reserved", ctypes.c_int32),
     ]
 
 
@@ -60,6 +74,7 @@ class Stats(ctypes.Structure):
         ("cyc_apply", ctypes.c_uint64),
         ("cyc_stage", ctypes.c_uint64),
         ("cyc_init", ctypes.c_uint64),
+        ("pt_swaps", ctypes.c_uint64),
     ]
 
     def as_dict(self):
@@ -99,6 +114,8 @@ def load():
     lib.osa_problem_size.argtypes = [vp, P(i32), P(i32), P(i32)]
     lib.osa_anneal.argtypes = [vp, vp, P(AnnealParams), vp, vp, vp, P(ctypes.c_double), P(u64),
                                P(Stats)]
+    lib.osa_pt_anneal.argtypes = [vp, vp, P(PtParams), vp, vp, vp, P(ctypes.c_double), P(u64),
+                                  P(Stats)]
     lib.osa_energy_batch.argtypes = [vp, vp, u64, vp]
     lib.osa_host_alloc_pinned.argtypes = [sz, P(vp)]
     lib.osa_host_free_pinned.argtypes = [vp]

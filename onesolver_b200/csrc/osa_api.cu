@@ -11,6 +11,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <limits>
 #include <vector>
 
 #include "osa_common.cuh"
@@ -569,7 +570,7 @@ int osa_anneal(osa_problem *p, const double *beta_schedule, const osa_anneal_par
   } else {
     auto run = [&](auto tag) -> cudaError_t {
       using T = decltype(tag);
-      DenseParams<T> dp;
+      DenseParams<T> dp{};
       dp.qoff = (const T *)p->d_qoff;
       dp.diag = (const T *)p->d_diag;
       dp.tscale = (const T *)p->d_tscale;
@@ -651,6 +652,244 @@ int osa_anneal(osa_problem *p, const double *beta_schedule, const osa_anneal_par
     stats->grid = info.grid;
     stats->launches = launches;
   }
+  return OSA_OK;
+}
+
+int osa_pt_anneal(osa_problem *p, const double *betas, const osa_pt_params *prm,
+                  double *best_energies, uint32_t *best_states_packed, uint8_t *best_state,
+                  double *best_energy, uint64_t *best_index, osa_stats *stats) {
+  if (!p || !betas || !prm) return fail(OSA_ERR_INVALID, "null argument");
+  if (prm->num_groups < 1) return fail(OSA_ERR_INVALID, "num_groups must be >= 1");
+  if (prm->num_replicas < 1 || prm->num_replicas > 4096)
+    return fail(OSA_ERR_INVALID, "num_replicas must be in 1..4096");
+  if (prm->num_rounds < 1) return fail(OSA_ERR_INVALID, "num_rounds must be >= 1");
+  if (prm->sweeps_per_round < 1) return fail(OSA_ERR_INVALID, "sweeps_per_round must be >= 1");
+  if (prm->flags != 0) return fail(OSA_ERR_INVALID, "unknown flags 0x%x", prm->flags);
+  if (prm->accept_rule != OSA_ACCEPT_REFERENCE && prm->accept_rule != OSA_ACCEPT_BOLTZMANN)
+    return fail(OSA_ERR_INVALID, "unknown accept rule %d", prm->accept_rule);
+  if ((uint64_t)prm->num_rounds * (uint64_t)prm->sweeps_per_round >= (1ull << 32))
+    return fail(OSA_ERR_INVALID, "num_rounds * sweeps_per_round must be < 2^32");
+  const int M = prm->num_replicas;
+  if (prm->num_groups > (1ull << 40) || (prm->first_group + prm->num_groups) > (1ull << 40))
+    return fail(OSA_ERR_INVALID, "group ids must stay below 2^40");
+  for (int j = 0; j < M; ++j) {
+    if (!(betas[j] > 0.0) || !std::isfinite(betas[j]))
+      return fail(OSA_ERR_INVALID, "betas[%d] = %g is not a positive finite number", j, betas[j]);
+    if (j > 0 && !(betas[j] > betas[j - 1]))
+      return fail(OSA_ERR_INVALID, "betas must be strictly increasing (betas[%d] <= betas[%d])", j,
+                  j - 1);
+  }
+  const bool f32 = p->prec == OSA_SWEEP_F32;
+  if (p->sparse || !dense_seq_supported(p->n, f32 ? 4 : 8))
+    return fail(OSA_ERR_UNSUPPORTED,
+                "parallel tempering runs on dense problems with n <= %d (this sweep precision)",
+                f32 ? 8192 : 4096);
+  const uint64_t tries = prm->num_groups * (uint64_t)M;
+  const uint64_t first_try = prm->first_group * (uint64_t)M;
+
+  int rc = select_device(p->device);
+  if (rc) return rc;
+  rc = ensure_workspace(p, tries, 1);
+  if (rc) return rc;
+
+  // ladder: threshold scale per rung (accept iff dE < tscale * (-ln u)) and the differences of the
+  // inverse temperatures that weigh the exchanges
+  std::vector<double> ts64(M), dinv(M, 0.0);
+  std::vector<float> ts32(M);
+  for (int j = 0; j < M; ++j) {
+    ts64[j] = prm->accept_rule == OSA_ACCEPT_REFERENCE ? betas[j] : 1.0 / betas[j];
+    ts32[j] = (float)ts64[j];
+  }
+  for (int j = 0; j + 1 < M; ++j) {
+    const double bj = prm->accept_rule == OSA_ACCEPT_REFERENCE ? 1.0 / betas[j] : betas[j];
+    const double bk = prm->accept_rule == OSA_ACCEPT_REFERENCE ? 1.0 / betas[j + 1] : betas[j + 1];
+    dinv[j] = bj - bk;
+  }
+  std::vector<int32_t> rung(tries);
+  for (uint64_t t = 0; t < tries; ++t) rung[t] = (int32_t)(t % (uint64_t)M);
+
+  const size_t esz = f32 ? 4 : 8;
+  const size_t words = (size_t)tries * p->nw;
+  uint32_t *d_cur = nullptr, *d_keep = nullptr;
+  double *d_ecur = nullptr, *d_beste = nullptr, *d_dinv = nullptr;
+  void *d_ts_traj = nullptr, *d_ts_rung = nullptr;
+  int32_t *d_temp_of_slot = nullptr, *d_slot_of_temp = nullptr;
+  unsigned long long *d_swaps = nullptr;
+  cudaStream_t st = p->stream;
+  auto release = [&]() {
+    dev_free(d_cur, st);
+    dev_free(d_keep, st);
+    dev_free(d_ecur, st);
+    dev_free(d_beste, st);
+    dev_free(d_dinv, st);
+    dev_free((char *)d_ts_traj, st);
+    dev_free((char *)d_ts_rung, st);
+    dev_free(d_temp_of_slot, st);
+    dev_free(d_slot_of_temp, st);
+    dev_free(d_swaps, st);
+  };
+#define PT_TRY(expr)                                                                        \
+  do {                                                                                      \
+    cudaError_t e_ = (expr);                                                                \
+    if (e_ != cudaSuccess) {                                                                \
+      release();                                                                            \
+      return fail(e_ == cudaErrorMemoryAllocation ? OSA_ERR_NOMEM : OSA_ERR_CUDA,           \
+                  "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), "osa_api.cu", __LINE__); \
+    }                                                                                       \
+  } while (0)
+  PT_TRY(dev_alloc(&d_cur, words * sizeof(uint32_t), st));
+  PT_TRY(dev_alloc(&d_keep, words * sizeof(uint32_t), st));
+  PT_TRY(dev_alloc(&d_ecur, tries * sizeof(double), st));
+  PT_TRY(dev_alloc(&d_beste, tries * sizeof(double), st));
+  PT_TRY(dev_alloc(&d_dinv, (size_t)M * sizeof(double), st));
+  PT_TRY(dev_alloc((char **)&d_ts_traj, tries * esz, st));
+  PT_TRY(dev_alloc((char **)&d_ts_rung, (size_t)M * esz, st));
+  PT_TRY(dev_alloc(&d_temp_of_slot, tries * sizeof(int32_t), st));
+  PT_TRY(dev_alloc(&d_slot_of_temp, tries * sizeof(int32_t), st));
+  PT_TRY(dev_alloc(&d_swaps, sizeof(unsigned long long), st));
+
+  PT_TRY(cudaMemcpyAsync(d_dinv, dinv.data(), (size_t)M * sizeof(double), cudaMemcpyHostToDevice, st));
+  PT_TRY(cudaMemcpyAsync(d_ts_rung, f32 ? (const void *)ts32.data() : (const void *)ts64.data(),
+                         (size_t)M * esz, cudaMemcpyHostToDevice, st));
+  PT_TRY(cudaMemcpyAsync(d_temp_of_slot, rung.data(), tries * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  PT_TRY(cudaMemcpyAsync(d_slot_of_temp, rung.data(), tries * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  {
+    // slot k starts on rung k
+    std::vector<unsigned char> init(tries * esz);
+    for (uint64_t t = 0; t < tries; ++t) {
+      if (f32) ((float *)init.data())[t] = ts32[t % (uint64_t)M];
+      else ((double *)init.data())[t] = ts64[t % (uint64_t)M];
+    }
+    PT_TRY(cudaMemcpyAsync(d_ts_traj, init.data(), tries * esz, cudaMemcpyHostToDevice, st));
+    PT_TRY(cudaStreamSynchronize(st));  // `init` goes out of scope
+  }
+  {
+    std::vector<double> inf(tries, std::numeric_limits<double>::infinity());
+    PT_TRY(cudaMemcpyAsync(d_beste, inf.data(), tries * sizeof(double), cudaMemcpyHostToDevice, st));
+    PT_TRY(cudaStreamSynchronize(st));
+  }
+  PT_TRY(cudaMemsetAsync(p->d_counters, 0, sizeof(Counters), st));
+  PT_TRY(cudaMemsetAsync(d_swaps, 0, sizeof(unsigned long long), st));
+
+  LaunchInfo info = {0, 0, 0, 0};
+  int launches = 0;
+  float ms_sweep = 0.f, ms_energy = 0.f;
+  PT_TRY(cudaEventRecord(p->ev[0], st));
+  PT_TRY(launch_pt_init_states(prm->seed, first_try, tries, p->n, p->nw, d_cur, st));
+  ++launches;
+  rc = exact_energies(p, d_cur, tries, d_ecur);
+  if (rc) {
+    release();
+    return rc;
+  }
+  ++launches;
+  for (int round = 0; round < prm->num_rounds; ++round) {
+    auto run = [&](auto tag) -> cudaError_t {
+      using T = decltype(tag);
+      DenseParams<T> dp{};
+      dp.qoff = (const T *)p->d_qoff;
+      dp.diag = (const T *)p->d_diag;
+      dp.tscale = nullptr;
+      dp.ld = p->ld;
+      dp.n = p->n;
+      dp.num_iter = 1;
+      dp.sweeps_per_beta = prm->sweeps_per_round;
+      dp.mode = OSA_MODE_SEQUENTIAL_SWEEP;
+      dp.seed = prm->seed;
+      dp.first_try = first_try;
+      dp.num_tries = tries;
+      dp.best_rel = p->d_best_rel;
+      dp.best_states = p->d_states;
+      dp.nw = p->nw;
+      dp.counters = p->d_counters;
+      dp.init_states = d_cur;
+      dp.final_states = d_cur;
+      dp.tscale_traj = (const T *)d_ts_traj;
+      dp.step_base = (uint32_t)round * (uint32_t)prm->sweeps_per_round;
+      return launch_dense_seq_ws<T>(dp, st, &info);
+    };
+    PT_TRY(f32 ? run(float()) : run(double()));
+    // best state of the round against the best kept so far (e_cur = energy the round started from)
+    PT_TRY(launch_pt_track_best(d_ecur, p->d_best_rel, p->d_states, tries, p->nw, d_beste, d_keep, st));
+    rc = exact_energies(p, d_cur, tries, d_ecur);
+    if (rc) {
+      release();
+      return rc;
+    }
+    if (f32)
+      PT_TRY(launch_pt_swap<float>(prm->seed, prm->first_group, prm->num_groups, M, (uint32_t)round,
+                                   d_ecur, d_dinv, (const float *)d_ts_rung, d_temp_of_slot,
+                                   d_slot_of_temp, (float *)d_ts_traj, d_swaps, st));
+    else
+      PT_TRY(launch_pt_swap<double>(prm->seed, prm->first_group, prm->num_groups, M, (uint32_t)round,
+                                    d_ecur, d_dinv, (const double *)d_ts_rung, d_temp_of_slot,
+                                    d_slot_of_temp, (double *)d_ts_traj, d_swaps, st));
+    launches += 4;
+  }
+  PT_TRY(cudaEventRecord(p->ev[1], st));
+  // exact energies of the kept best states, then the usual argmin (lowest id wins ties)
+  rc = exact_energies(p, d_keep, tries, p->d_energy);
+  if (rc) {
+    release();
+    return rc;
+  }
+  ++launches;
+  PT_TRY(cudaEventRecord(p->ev[2], st));
+  PT_TRY(launch_argmin(p->d_energy, tries, p->d_arg_idx, p->d_arg_e, st));
+  ++launches;
+  PT_TRY(cudaEventRecord(p->ev[3], st));
+
+  unsigned long long h_idx = 0, h_swaps = 0;
+  double h_e = 0.0;
+  Counters h_cnt;
+  PT_TRY(cudaMemcpyAsync(&h_idx, p->d_arg_idx, sizeof(h_idx), cudaMemcpyDeviceToHost, st));
+  PT_TRY(cudaMemcpyAsync(&h_e, p->d_arg_e, sizeof(h_e), cudaMemcpyDeviceToHost, st));
+  PT_TRY(cudaMemcpyAsync(&h_cnt, p->d_counters, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+  PT_TRY(cudaMemcpyAsync(&h_swaps, d_swaps, sizeof(h_swaps), cudaMemcpyDeviceToHost, st));
+  {
+    cudaError_t sync_err = cudaStreamSynchronize(st);
+    if (sync_err != cudaSuccess) {
+      release();
+      return fail(OSA_ERR_CUDA, "parallel tempering kernels failed: %s", cudaGetErrorString(sync_err));
+    }
+  }
+  if (h_idx >= tries) {
+    release();
+    return fail(OSA_ERR_CUDA, "argmin returned an invalid index");
+  }
+  if (best_energies)
+    PT_TRY(cudaMemcpyAsync(best_energies, p->d_energy, tries * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (best_states_packed)
+    PT_TRY(cudaMemcpyAsync(best_states_packed, d_keep, words * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  std::vector<uint32_t> win(p->nw);
+  PT_TRY(cudaMemcpyAsync(win.data(), d_keep + (size_t)h_idx * p->nw, (size_t)p->nw * sizeof(uint32_t),
+                         cudaMemcpyDeviceToHost, st));
+  PT_TRY(cudaStreamSynchronize(st));
+  if (best_state)
+    for (int i = 0; i < p->n; ++i) best_state[i] = (uint8_t)((win[i >> 5] >> (i & 31)) & 1u);
+  if (best_energy) *best_energy = h_e;
+  if (best_index) *best_index = first_try + h_idx;
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->attempts = (uint64_t)prm->num_rounds * (uint64_t)prm->sweeps_per_round * (uint64_t)p->n * tries;
+    stats->accepts = h_cnt.accepts;
+    stats->row_fetches = h_cnt.row_fetches;
+    stats->init_row_fetches = h_cnt.init_row_fetches;
+    stats->pt_swaps = h_swaps;
+    cudaEventElapsedTime(&ms_sweep, p->ev[0], p->ev[1]);
+    cudaEventElapsedTime(&ms_energy, p->ev[1], p->ev[2]);
+    stats->ms_sweep = ms_sweep;
+    stats->ms_energy = ms_energy;
+    cudaEventElapsedTime(&stats->ms_reduce, p->ev[2], p->ev[3]);
+    cudaEventElapsedTime(&stats->ms_total, p->ev[0], p->ev[3]);
+    stats->kernel_id = KID_DENSE_SEQ;
+    stats->traj_per_batch = info.traj_per_batch;
+    stats->q_elem_bytes = f32 ? 4 : 8;
+    stats->grid = info.grid;
+    stats->launches = launches;
+  }
+  release();
+#undef PT_TRY
   return OSA_OK;
 }
 

@@ -18,9 +18,10 @@ namespace osa {
 //                (replaces random.bit(), reference annealing.hpp:90-92)
 //   STREAM_SEQ : c0 = site>>2, c1 = sweep -> word site&3 = uniform for (sweep, site)
 //   STREAM_RND : c0 = 0, c1 = step        -> word0 = site draw, word1 = uniform
+//   STREAM_PT  : c0 = pair, c1 = round (traj = group id) -> word0 = uniform of a replica swap
 //                (replaces bit_index()/uniform(), reference annealing.hpp:101,108)
 // ---------------------------------------------------------------------------
-enum : uint32_t { STREAM_INIT = 0, STREAM_SEQ = 1, STREAM_RND = 2 };
+enum : uint32_t { STREAM_INIT = 0, STREAM_SEQ = 1, STREAM_RND = 2, STREAM_PT = 3 };
 
 struct U4 { uint32_t x, y, z, w; };
 
@@ -151,6 +152,12 @@ struct DenseParams {
   uint32_t *best_states;    // [num_tries][nw]
   int nw;                   // words per state = ceil(n/32)
   Counters *counters;
+  // resumable rounds (parallel tempering, osa_pt_anneal); all optional, zero = plain annealing.
+  // Honoured by k_dense_seq_ws only.
+  const uint32_t *init_states;  // [num_tries][nw]: start from these spins instead of STREAM_INIT
+  const T *tscale_traj;         // [num_tries]: per-trajectory threshold scale, replaces tscale[iter]
+  uint32_t *final_states;       // [num_tries][nw]: spins after the last sweep (may alias init_states)
+  uint32_t step_base;           // first sweep number of this launch in the STREAM_SEQ counter
 };
 
 template <typename T>
@@ -195,6 +202,16 @@ template <typename T>
 cudaError_t launch_dense_generic(const DenseParams<T> &p, cudaStream_t s, LaunchInfo *info);
 template <typename T>
 cudaError_t launch_sparse(const SparseParams<T> &p, cudaStream_t s, LaunchInfo *info);
+cudaError_t launch_pt_init_states(uint64_t seed, uint64_t first_try, uint64_t num_tries, int n,
+                                  int nw, uint32_t *states, cudaStream_t s);
+cudaError_t launch_pt_track_best(const double *e_start, const double *best_rel,
+                                 const uint32_t *round_best, uint64_t num_tries, int nw,
+                                 double *best_e, uint32_t *best_keep, cudaStream_t s);
+template <typename T>
+cudaError_t launch_pt_swap(uint64_t seed, uint64_t first_group, uint64_t num_groups, int replicas,
+                           uint32_t round, const double *e_cur, const double *dinv,
+                           const T *tscale_of_temp, int32_t *temp_of_slot, int32_t *slot_of_temp,
+                           T *tscale_traj, unsigned long long *swap_count, cudaStream_t s);
 bool dense_seq_supported(int n, int elem_bytes);
 bool dense_generic_supported(int n, int elem_bytes);
 size_t sparse_ws_words(int n, uint64_t num_tries);

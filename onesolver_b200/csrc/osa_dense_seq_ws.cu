@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_dense_seq_ws(const DenseParam
   // per-trajectory walk state of the decide warps (indexed by a run-time trajectory number, so it
   // lives here rather than in a register array that the compiler would demote to local memory)
   __shared__ double s_erel[R], s_best[R];
+  __shared__ T s_ts[R];  // per-trajectory threshold scale (only with p.tscale_traj)
   __shared__ uint32_t s_atbest[R];
   __shared__ uint32_t s_x[R][NWP];
   __shared__ uint32_t s_xb[R][NWP];
@@ -169,14 +170,20 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_dense_seq_ws(const DenseParam
         for (int k = lane; k < NWP; k += 32) {
           uint32_t word = 0;
           if (tv && k < nblk) {
-            const U4 d = engine_draw(p.seed, traj, STREAM_INIT, (uint32_t)k >> 2, 0u);
-            word = pick(d, (uint32_t)k & 3u);
+            if (p.init_states) {  // resume: the spins a previous launch left in final_states
+              word = p.init_states[(batch0 + (uint64_t)r) * (uint64_t)p.nw + k];
+            } else {
+              const U4 d = engine_draw(p.seed, traj, STREAM_INIT, (uint32_t)k >> 2, 0u);
+              word = pick(d, (uint32_t)k & 3u);
+            }
             const int valid = n - k * 32;
             if (valid < 32) word &= (1u << valid) - 1u;
           }
           s_x[r][k] = word;
           s_xb[r][k] = word;
         }
+        if (lane == 0)
+          s_ts[r] = (p.tscale_traj && tv) ? p.tscale_traj[batch0 + (uint64_t)r] : (T)0;
       }
     }
     for (int r = dt; r < R; r += WS_DECIDE_WARPS * 32) {
@@ -226,7 +233,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_dense_seq_ws(const DenseParam
           }
           uint32_t xw = s_x[r][b];
           const U4 d = engine_draw(p.seed, traj, STREAM_SEQ, (uint32_t)site >> 2, step);
-          const T theta = threshold<T>(ts, pick(d, (uint32_t)site & 3u));
+          const T theta = threshold<T>(p.tscale_traj ? s_ts[r] : ts, pick(d, (uint32_t)site & 3u));
           const bool lane_ok = tv && site < n;
           uint32_t acc = 0, sg = 0, from = 0xffffffffu;
           double erel = s_erel[r], best = s_best[r];
@@ -274,10 +281,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_dense_seq_ws(const DenseParam
     };
 
     long long g = 0;
-    uint32_t step = 0;
+    uint32_t step = p.step_base;
     long long t_mark = clock64();
     for (int iter = 0; iter < p.num_iter; ++iter) {
-      const T ts = p.tscale[iter];
+      const T ts = p.tscale_traj ? (T)0 : p.tscale[iter];
       for (int sw = 0; sw < p.sweeps_per_beta; ++sw, ++step) {
         for (int b = 0; b < nblk; ++b, ++g) {
           decide(g, b, step, ts);
@@ -298,6 +305,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_dense_seq_ws(const DenseParam
         __syncwarp();
         const uint64_t tl = batch0 + (uint64_t)r;
         for (int k = lane; k < p.nw; k += 32) p.best_states[tl * (uint64_t)p.nw + k] = s_xb[r][k];
+        if (p.final_states)
+          for (int k = lane; k < p.nw; k += 32) p.final_states[tl * (uint64_t)p.nw + k] = s_x[r][k];
         if (lane == 0) p.best_rel[tl] = s_best[r];
       }
     }

@@ -58,6 +58,8 @@ def load():
     dense = [vp, vp, i32, sz, vp, i32, i32, i32, u64, u64, u64, i32, vp, vp, vp, P(Counters)]
     lib.orc_replay_dense_f32.argtypes = dense
     lib.orc_replay_dense_f64.argtypes = dense
+    lib.orc_replay_dense_f32_round.argtypes = dense + [vp, vp, u32]
+    lib.orc_replay_dense_f64_round.argtypes = dense + [vp, vp, u32]
     csr = [vp, vp, vp, vp, i32, vp, i32, i32, i32, u64, u64, u64, vp, vp, vp, P(Counters)]
     lib.orc_replay_csr_f32.argtypes = csr
     lib.orc_replay_csr_f64.argtypes = csr
@@ -174,6 +176,34 @@ def replay_dense(qsym, schedule, num_iter, num_tries, sweeps_per_beta=1, mode=0,
     if rc != 0:
         raise ValueError("orc_replay_dense failed")
     return best_rel, best, final, cnt
+
+
+def engine_draw(seed, traj, stream, c0, c1):
+    out = np.zeros(4, dtype=np.uint32)
+    load().orc_engine_draw(int(seed), int(traj), int(stream), int(c0), int(c1), out.ctypes.data)
+    return out
+
+
+def replay_dense_round(qoff, diag, ts_traj, init_states, sweeps, seed, first_try, step_base):
+    """One resumable launch of the dense sweep kernel (sequential sweeps, per-trajectory
+    threshold scale, start states given): -> (best_rel, best_states, final_states)."""
+    lib = load()
+    dtype = qoff.dtype.type
+    n = qoff.shape[0]
+    nw = (n + 31) // 32
+    tries = init_states.shape[0]
+    ts = np.ascontiguousarray(ts_traj, dtype=dtype)
+    init = np.ascontiguousarray(init_states, dtype=np.uint32)
+    best_rel = np.zeros(tries, dtype=np.float64)
+    best = np.zeros((tries, nw), dtype=np.uint32)
+    final = np.zeros((tries, nw), dtype=np.uint32)
+    fn = lib.orc_replay_dense_f32_round if dtype == np.float32 else lib.orc_replay_dense_f64_round
+    rc = fn(qoff.ctypes.data, diag.ctypes.data, n, qoff.shape[1], None, 1, sweeps, 1, seed,
+            first_try, tries, 1, best_rel.ctypes.data, best.ctypes.data, final.ctypes.data, None,
+            init.ctypes.data, ts.ctypes.data, step_base)
+    if rc != 0:
+        raise ValueError("orc_replay_dense_round failed")
+    return best_rel, best, final
 
 
 def replay_csr(rowptr, col, val, diag, schedule, num_iter, num_tries, sweeps_per_beta=1, mode=1,

@@ -314,11 +314,27 @@ static void init_state_packed(uint64_t seed, uint64_t traj, int n, uint32_t *x) 
 
 /* The dense and CSR replays are generated for float and double from one macro
  * body so both precisions follow literally the same statement order.         */
+/* The _round variant adds what a resumable launch of the CUDA kernel takes (osa_pt_anneal):    \
+ * init_states (NULL: STREAM_INIT), tscale_traj (NULL: tscale[iter]), step_base.             */ \
 #define DEFINE_REPLAY_DENSE(NAME, T, FMA)                                                       \
+  int NAME##_round(const T *qoff, const T *diag, int n, size_t ld, const T *tscale, int num_iter,\
+           int sweeps_per_beta, int mode, uint64_t seed, uint64_t first_try, uint64_t num_tries, \
+           int batch_r, double *best_rel, uint32_t *best_states_packed,                          \
+           uint32_t *final_states_packed, orc_counters *counters,                                \
+           const uint32_t *init_states, const T *tscale_traj, uint32_t step_base);               \
   int NAME(const T *qoff, const T *diag, int n, size_t ld, const T *tscale, int num_iter,       \
            int sweeps_per_beta, int mode, uint64_t seed, uint64_t first_try, uint64_t num_tries, \
            int batch_r, double *best_rel, uint32_t *best_states_packed,                          \
            uint32_t *final_states_packed, orc_counters *counters) {                              \
+    return NAME##_round(qoff, diag, n, ld, tscale, num_iter, sweeps_per_beta, mode, seed,        \
+                        first_try, num_tries, batch_r, best_rel, best_states_packed,             \
+                        final_states_packed, counters, NULL, NULL, 0u);                          \
+  }                                                                                              \
+  int NAME##_round(const T *qoff, const T *diag, int n, size_t ld, const T *tscale, int num_iter,\
+           int sweeps_per_beta, int mode, uint64_t seed, uint64_t first_try, uint64_t num_tries, \
+           int batch_r, double *best_rel, uint32_t *best_states_packed,                          \
+           uint32_t *final_states_packed, orc_counters *counters,                                \
+           const uint32_t *init_states, const T *tscale_traj, uint32_t step_base) {              \
     if (n <= 0 || num_iter <= 0 || sweeps_per_beta <= 0) return -1;                              \
     const int nw = (n + 31) / 32;                                                                \
     if (mode == ORC_MODE_RANDOM_SITE || batch_r < 1) batch_r = 1;                                \
@@ -338,7 +354,8 @@ static void init_state_packed(uint64_t seed, uint64_t traj, int n, uint32_t *x) 
         uint64_t tl = (uint64_t)b * (uint64_t)batch_r + (uint64_t)rr;                            \
         if (tl >= num_tries) break;                                                              \
         uint64_t traj = first_try + tl;                                                          \
-        init_state_packed(seed, traj, n, x);                                                     \
+        if (init_states) memcpy(x, init_states + (size_t)tl * nw, sizeof(uint32_t) * (size_t)nw);\
+        else init_state_packed(seed, traj, n, x);                                                \
         memcpy(xb, x, sizeof(uint32_t) * (size_t)nw);                                            \
         /* initial local field: h = diag, then add rows of set spins in index order */           \
         for (int j = 0; j < n; ++j) h[j] = diag[j];                                              \
@@ -350,9 +367,9 @@ static void init_state_packed(uint64_t seed, uint64_t traj, int n, uint32_t *x) 
         }                                                                                        \
         double erel = 0.0, best = 0.0;                                                           \
         uint64_t sidx = 0;                                                                       \
-        uint32_t step = 0;                                                                       \
+        uint32_t step = step_base;                                                               \
         for (int iter = 0; iter < num_iter; ++iter) {                                            \
-          const T ts = tscale[iter];                                                             \
+          const T ts = tscale_traj ? tscale_traj[tl] : tscale[iter];                             \
           for (int sw = 0; sw < sweeps_per_beta; ++sw, ++step) {                                 \
             const int n_sites = (mode == ORC_MODE_SEQUENTIAL_SWEEP) ? n : 1;                     \
             for (int s = 0; s < n_sites; ++s, ++sidx) {                                          \

@@ -119,6 +119,23 @@ int orc_replay_dense_f64(const double *qoff, const double *diag, int n, size_t l
                          double *best_rel, uint32_t *best_states_packed,
                          uint32_t *final_states_packed, orc_counters *counters);
 
+/* resumable variants (osa_pt_anneal): init_states NULL = STREAM_INIT, tscale_traj NULL =
+ * tscale[iter], step_base = first sweep number in the STREAM_SEQ counter            */
+int orc_replay_dense_f32_round(const float *qoff, const float *diag, int n, size_t ld,
+                               const float *tscale, int num_iter, int sweeps_per_beta, int mode,
+                               uint64_t seed, uint64_t first_try, uint64_t num_tries, int batch_r,
+                               double *best_rel, uint32_t *best_states_packed,
+                               uint32_t *final_states_packed, orc_counters *counters,
+                               const uint32_t *init_states, const float *tscale_traj,
+                               uint32_t step_base);
+int orc_replay_dense_f64_round(const double *qoff, const double *diag, int n, size_t ld,
+                               const double *tscale, int num_iter, int sweeps_per_beta, int mode,
+                               uint64_t seed, uint64_t first_try, uint64_t num_tries, int batch_r,
+                               double *best_rel, uint32_t *best_states_packed,
+                               uint32_t *final_states_packed, orc_counters *counters,
+                               const uint32_t *init_states, const double *tscale_traj,
+                               uint32_t step_base);
+
 /* CSR replay (local field recomputed on demand in CSR order, like the CUDA
  * sparse kernel).  Symmetric adjacency, no diagonal entries.                   */
 int orc_replay_csr_f32(const int32_t *rowptr, const int32_t *col, const float *val,

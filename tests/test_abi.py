@@ -25,12 +25,13 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert sorted(capi.EXPORTED_SYMBOLS) == names
-    assert lib.osa_abi_version() == 1
+    assert lib.osa_abi_version() == 2
 
 
 def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(capi.AnnealParams) == 48
-    assert ctypes.sizeof(capi.Stats) == 104
+    assert ctypes.sizeof(capi.Stats) == 112
+    assert ctypes.sizeof(capi.PtParams) == 48
 
 
 def test_no_cpu_fallback_without_a_device():
