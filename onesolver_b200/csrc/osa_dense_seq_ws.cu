@@ -37,7 +37,10 @@ __device__ __forceinline__ void bar_decide() {
   asm volatile("bar.sync 2, %0;" ::"n"(WS_DECIDE_WARPS * 32) : "memory");
 }
 
-template <typename T, int NCH, int R, int K, int G>
+// PT: resumable launch for parallel tempering (start spins from memory, per-trajectory threshold
+// scale, final spins written back, running sweep counter); a separate instantiation so that the
+// plain annealing kernel carries none of it.
+template <typename T, int NCH, int R, int K, int G, bool PT>
 __global__ void __launch_bounds__(WS_THREADS, 1) k_dense_seq_ws(const DenseParams<T> p) {
   constexpr int TH = WS_APPLY_THREADS;
   using C = Cfg<T, NCH, R, TH>;
@@ -170,7 +173,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_dense_seq_ws(const DenseParam
         for (int k = lane; k < NWP; k += 32) {
           uint32_t word = 0;
           if (tv && k < nblk) {
-            if (p.init_states) {  // resume: the spins a previous launch left in final_states
+            if (PT && p.init_states) {  // resume: the spins a previous launch left in final_states
               word = p.init_states[(batch0 + (uint64_t)r) * (uint64_t)p.nw + k];
             } else {
               const U4 d = engine_draw(p.seed, traj, STREAM_INIT, (uint32_t)k >> 2, 0u);
@@ -182,7 +185,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_dense_seq_ws(const DenseParam
           s_x[r][k] = word;
           s_xb[r][k] = word;
         }
-        if (lane == 0)
+        if (PT && lane == 0)
           s_ts[r] = (p.tscale_traj && tv) ? p.tscale_traj[batch0 + (uint64_t)r] : (T)0;
       }
     }
@@ -233,7 +236,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_dense_seq_ws(const DenseParam
           }
           uint32_t xw = s_x[r][b];
           const U4 d = engine_draw(p.seed, traj, STREAM_SEQ, (uint32_t)site >> 2, step);
-          const T theta = threshold<T>(p.tscale_traj ? s_ts[r] : ts, pick(d, (uint32_t)site & 3u));
+          const T theta = threshold<T>(PT ? s_ts[r] : ts, pick(d, (uint32_t)site & 3u));
           const bool lane_ok = tv && site < n;
           uint32_t acc = 0, sg = 0, from = 0xffffffffu;
           double erel = s_erel[r], best = s_best[r];
@@ -281,10 +284,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_dense_seq_ws(const DenseParam
     };
 
     long long g = 0;
-    uint32_t step = p.step_base;
+    uint32_t step = PT ? p.step_base : 0u;
     long long t_mark = clock64();
     for (int iter = 0; iter < p.num_iter; ++iter) {
-      const T ts = p.tscale_traj ? (T)0 : p.tscale[iter];
+      const T ts = PT ? (T)0 : p.tscale[iter];
       for (int sw = 0; sw < p.sweeps_per_beta; ++sw, ++step) {
         for (int b = 0; b < nblk; ++b, ++g) {
           decide(g, b, step, ts);
@@ -305,7 +308,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_dense_seq_ws(const DenseParam
         __syncwarp();
         const uint64_t tl = batch0 + (uint64_t)r;
         for (int k = lane; k < p.nw; k += 32) p.best_states[tl * (uint64_t)p.nw + k] = s_xb[r][k];
-        if (p.final_states)
+        if (PT && p.final_states)
           for (int k = lane; k < p.nw; k += 32) p.final_states[tl * (uint64_t)p.nw + k] = s_x[r][k];
         if (lane == 0) p.best_rel[tl] = s_best[r];
       }
@@ -322,7 +325,8 @@ cudaError_t launch_ws(const DenseParams<T> &p, cudaStream_t s, LaunchInfo *info)
   const uint64_t grid64 = (p.num_tries + R - 1) / R;
   if (grid64 == 0 || grid64 > 0x7fffffffull) return cudaErrorInvalidValue;
   const size_t smem = (size_t)K * NCH * WS_APPLY_THREADS * 16;
-  auto kern = k_dense_seq_ws<T, NCH, R, K, G>;
+  // the resumable instantiation only when a per-trajectory scale is given (osa_pt_anneal)
+  auto kern = p.tscale_traj ? k_dense_seq_ws<T, NCH, R, K, G, true> : k_dense_seq_ws<T, NCH, R, K, G, false>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
   kern<<<(unsigned)grid64, WS_THREADS, smem, s>>>(p);
