@@ -50,12 +50,18 @@ def parse_args():
 
 # --------------------------------------------------------------------------- helpers
 def sm_count(device):
-    """Number of SMs of the device (torch is only asked for the device property)."""
+    """Number of SMs of the device, asked from the CUDA runtime the engine library already loaded."""
+    import ctypes
     try:
-        import torch
-        return torch.cuda.get_device_properties(device).multi_processor_count
-    except Exception:
-        return 148  # B200
+        from onesolver_b200 import capi
+        capi.load()
+        rt = ctypes.CDLL("libcudart.so.12")
+        value = ctypes.c_int(0)
+        if rt.cudaDeviceGetAttribute(ctypes.byref(value), 16, int(device)) == 0 and value.value > 0:
+            return value.value  # 16 = cudaDevAttrMultiProcessorCount
+    except OSError:
+        pass
+    return 148  # B200
 
 
 def load_measured_peaks():
