@@ -98,6 +98,10 @@ def test_n24_fractional_coefficients(gpu):
     (100, np.float32, 50, 4), (300, np.float64, 40, 3), (513, np.float64, 20, 2),
     (1024, np.float32, 24, 2), (1100, np.float32, 17, 2), (1024, np.float64, 16, 2),
     (2100, np.float32, 9, 1), (2048, np.float64, 9, 1), (4096, np.float32, 8, 1),
+    # the remaining register/ring shapes of launch_dense_seq_ws (ld/1024 = 5..8, ld/512 = 5..8)
+    (5000, np.float32, 9, 1), (6100, np.float32, 9, 1), (7000, np.float32, 5, 1),
+    (8192, np.float32, 5, 1), (2500, np.float64, 7, 1), (3000, np.float64, 7, 1),
+    (3500, np.float64, 5, 1), (4096, np.float64, 5, 1),
 ])
 def test_dense_seq_bit_exact(gpu, n, dtype, tries, sweeps):
     q = gen.dense_uniform_qubo(n, seed=100 + n)
