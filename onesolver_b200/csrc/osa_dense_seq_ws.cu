@@ -29,20 +29,38 @@ using namespace dseq;
 namespace {
 
 constexpr int WS_APPLY_THREADS = 256;
-constexpr int WS_DECIDE_WARPS = 4;
-constexpr int WS_THREADS = WS_APPLY_THREADS + WS_DECIDE_WARPS * 32;
 
-__device__ __forceinline__ void bar_cta() { asm volatile("bar.sync 1, %0;" ::"n"(WS_THREADS) : "memory"); }
-__device__ __forceinline__ void bar_decide() {
-  asm volatile("bar.sync 2, %0;" ::"n"(WS_DECIDE_WARPS * 32) : "memory");
+// Register budgets of the two roles for DW decide warps.  The kernel is launched with
+// LAUNCH = 65536 / threads registers per thread (multiple of 8); the decide warps give up
+// LAUNCH - DECIDE each, and setmaxnreg.inc can only draw from what the CTA's own warps released,
+// so the apply warps get exactly LAUNCH + (LAUNCH - DECIDE) * decide_threads / apply_threads:
+//   DW = 4: 384 threads, 168 -> apply 224 / decide 56   (shapes with >= 192 field registers)
+//   DW = 8: 512 threads, 128 -> apply 200 / decide 56   (small N: the decisions are the bottleneck)
+template <int DW>
+struct WsRegs {
+  static constexpr int THREADS = WS_APPLY_THREADS + DW * 32;
+  static constexpr int LAUNCH = (65536 / THREADS) / 8 * 8;
+  static constexpr int DECIDE = 56;
+  static constexpr int APPLY_RAW = LAUNCH + (LAUNCH - DECIDE) * (DW * 32) / WS_APPLY_THREADS;
+  static constexpr int APPLY = (APPLY_RAW > 232 ? 232 : APPLY_RAW) / 8 * 8;
+};
+static_assert(WsRegs<4>::APPLY == 224 && WsRegs<8>::APPLY == 200, "register split");
+
+template <int THREADS>
+__device__ __forceinline__ void bar_named(int id) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(THREADS) : "memory");
 }
 
 // PT: resumable launch for parallel tempering (start spins from memory, per-trajectory threshold
 // scale, final spins written back, running sweep counter); a separate instantiation so that the
 // plain annealing kernel carries none of it.
-template <typename T, int NCH, int R, int K, int G, bool PT>
-__global__ void __launch_bounds__(WS_THREADS, 1) k_dense_seq_ws(const DenseParams<T> p) {
+template <typename T, int NCH, int R, int K, int G, bool PT, int DW>
+__global__ void __launch_bounds__(WsRegs<DW>::THREADS, 1) k_dense_seq_ws(const DenseParams<T> p) {
   constexpr int TH = WS_APPLY_THREADS;
+  constexpr int WS_DECIDE_WARPS = DW;
+  constexpr int WS_THREADS = WsRegs<DW>::THREADS;
+  auto bar_cta = [] { bar_named<WS_THREADS>(1); };
+  auto bar_decide = [] { bar_named<DW * 32>(2); };
   using C = Cfg<T, NCH, R, TH>;
   using VecT = typename C::VecT;
   constexpr int V = C::V, CPT = C::CPT, CHW = C::CHW, NWP = C::NWP;
@@ -73,7 +91,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_dense_seq_ws(const DenseParam
 
   if (tid < WS_APPLY_THREADS) {
     // =============================== APPLY ROLE ===============================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WsRegs<DW>::APPLY));
     Field<T, CPT> h[R];
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
@@ -159,7 +177,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_dense_seq_ws(const DenseParam
     }
   } else {
     // =============================== DECIDE ROLE ===============================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WsRegs<DW>::DECIDE));
     const int dt = tid - WS_APPLY_THREADS;  // 0..127
     const int lane = dt & 31, dwarp = dt >> 5;
 
@@ -320,13 +338,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_dense_seq_ws(const DenseParam
   }
 }
 
-template <typename T, int NCH, int R, int K, int G>
+template <typename T, int NCH, int R, int K, int G, int DW = 4>
 cudaError_t launch_ws(const DenseParams<T> &p, cudaStream_t s, LaunchInfo *info) {
+  constexpr int WS_THREADS = WsRegs<DW>::THREADS;
   const uint64_t grid64 = (p.num_tries + R - 1) / R;
   if (grid64 == 0 || grid64 > 0x7fffffffull) return cudaErrorInvalidValue;
   const size_t smem = (size_t)K * NCH * WS_APPLY_THREADS * 16;
   // the resumable instantiation only when a per-trajectory scale is given (osa_pt_anneal)
-  auto kern = p.tscale_traj ? k_dense_seq_ws<T, NCH, R, K, G, true> : k_dense_seq_ws<T, NCH, R, K, G, false>;
+  auto kern = p.tscale_traj ? k_dense_seq_ws<T, NCH, R, K, G, true, DW>
+                            : k_dense_seq_ws<T, NCH, R, K, G, false, DW>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
   kern<<<(unsigned)grid64, WS_THREADS, smem, s>>>(p);
@@ -339,6 +359,16 @@ cudaError_t launch_ws(const DenseParams<T> &p, cudaStream_t s, LaunchInfo *info)
   return cudaGetLastError();
 }
 
+// decide warps for the shapes with <= 3 column groups per thread (N <= 3072 fp32 / 1536 fp64),
+// where the decisions, not the row streaming, bound the kernel; OSA_WS_DW=4 for A/B runs
+int decide_warps_small_n() {
+  static const int dw = [] {
+    const char *e = getenv("OSA_WS_DW");
+    return (e && atoi(e) == 4) ? 4 : 8;
+  }();
+  return dw;
+}
+
 }  // namespace
 
 // same shape table as launch_dense_seq (osa_dense_seq.cu)
@@ -349,10 +379,11 @@ template <>
 cudaError_t launch_dense_seq_ws<float>(const DenseParams<float> &p, cudaStream_t s,
                                        LaunchInfo *info) {
   if (p.ld % 1024 != 0) return cudaErrorInvalidValue;
+  const bool dw8 = decide_warps_small_n() == 8;
   switch (p.ld / 1024) {
-    case 1: return launch_ws<float, 1, 16, 16, 4>(p, s, info);
-    case 2: return launch_ws<float, 2, 16, 16, 4>(p, s, info);
-    case 3: return launch_ws<float, 3, 12, 12, 4>(p, s, info);
+    case 1: return dw8 ? launch_ws<float, 1, 16, 16, 4, 8>(p, s, info) : launch_ws<float, 1, 16, 16, 4>(p, s, info);
+    case 2: return dw8 ? launch_ws<float, 2, 16, 16, 4, 8>(p, s, info) : launch_ws<float, 2, 16, 16, 4>(p, s, info);
+    case 3: return dw8 ? launch_ws<float, 3, 12, 12, 4, 8>(p, s, info) : launch_ws<float, 3, 12, 12, 4>(p, s, info);
     case 4: {
       const char *e = getenv("OSA_WS_R");  // tuning knob (tools/probe.py): trajectories per CTA
       const int r = e ? atoi(e) : 12;
@@ -372,10 +403,11 @@ template <>
 cudaError_t launch_dense_seq_ws<double>(const DenseParams<double> &p, cudaStream_t s,
                                         LaunchInfo *info) {
   if (p.ld % 512 != 0) return cudaErrorInvalidValue;
+  const bool dw8 = decide_warps_small_n() == 8;
   switch (p.ld / 512) {
-    case 1: return launch_ws<double, 1, 16, 16, 4>(p, s, info);
-    case 2: return launch_ws<double, 2, 16, 16, 4>(p, s, info);
-    case 3: return launch_ws<double, 3, 12, 12, 4>(p, s, info);
+    case 1: return dw8 ? launch_ws<double, 1, 16, 16, 4, 8>(p, s, info) : launch_ws<double, 1, 16, 16, 4>(p, s, info);
+    case 2: return dw8 ? launch_ws<double, 2, 16, 16, 4, 8>(p, s, info) : launch_ws<double, 2, 16, 16, 4>(p, s, info);
+    case 3: return dw8 ? launch_ws<double, 3, 12, 12, 4, 8>(p, s, info) : launch_ws<double, 3, 12, 12, 4>(p, s, info);
     case 4: return launch_ws<double, 4, 8, 12, 2>(p, s, info);
     case 5: return launch_ws<double, 5, 6, 9, 2>(p, s, info);
     case 6: return launch_ws<double, 6, 6, 8, 2>(p, s, info);

@@ -59,6 +59,10 @@ if "dense" in what:
     s = np.sqrt(1024)
     run_dense(1024, capi.SWEEP_F64, 148 * 16, 8, 0.3 * s, 0.02 * s, "dense1024_f64")
     run_dense(1024, capi.SWEEP_F32, 148 * 16, 8, 0.3 * s, 0.02 * s, "dense1024_f32")
+    s = np.sqrt(2048)
+    run_dense(2048, capi.SWEEP_F32, 148 * 16, 4, 0.3 * s, 0.02 * s, "dense2048_f32")
+    s = np.sqrt(512)
+    run_dense(512, capi.SWEEP_F64, 148 * 16, 16, 0.3 * s, 0.02 * s, "dense512_f64")
     run_dense(4096, capi.SWEEP_F64, 148 * 4, 2, 0.3 * 64, 0.02 * 64, "dense4096_f64")
 
 if "cfg" in what:
