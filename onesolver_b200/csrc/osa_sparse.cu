@@ -178,41 +178,51 @@ __global__ void k_sparse(const SparseParams<T> p, int x_words_per_warp) {
           const int e1 = __shfl_sync(0xffffffffu, rp_hi, min(31, n - b * 32 - 1));
           const bool staged = (e1 - e0) <= SP_CAP;
           const int i_end = min(32, n - b * 32);
-          for (int s = 0; s < i_end; ++s) {
-            const int i = b * 32 + s;
-            if ((i & 3) == 0) d = engine_draw(p.seed, traj, STREAM_SEQ, (uint32_t)i >> 2, step);
-            const T theta = threshold<T>(ts, pick(d, (uint32_t)i & 3u));
-            const int pb = __shfl_sync(0xffffffffu, rp_lo, s);
-            const int pe = __shfl_sync(0xffffffffu, rp_hi, s);
-            T hk = __shfl_sync(0xffffffffu, dg, s);
-            if (staged) {
-              const int32_t *sc = stage->col[buf] - e0;
-              const T *sv = stage->val[buf] - e0;
-#pragma unroll 4
-              for (int q = pb; q < pe; ++q) {
-                if ((X[sc[q]] >> lane) & 1u) hk = det::add(hk, sv[q]);
+          // one Philox block serves four consecutive sites: their four thresholds (a chain of
+          // ~40 dependent operations each) are computed together so the chains overlap, and sit
+          // off the critical path of three of the four site steps
+          for (int s4 = 0; s4 < i_end; s4 += 4) {
+            d = engine_draw(p.seed, traj, STREAM_SEQ, (uint32_t)(b * 32 + s4) >> 2, step);
+            const T th4[4] = {threshold<T>(ts, d.x), threshold<T>(ts, d.y), threshold<T>(ts, d.z),
+                              threshold<T>(ts, d.w)};
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const int s = s4 + k4;
+              if (s >= i_end) break;
+              const int i = b * 32 + s;
+              const T theta = th4[k4];
+              const int pb = __shfl_sync(0xffffffffu, rp_lo, s);
+              const int pe = __shfl_sync(0xffffffffu, rp_hi, s);
+              T hk = __shfl_sync(0xffffffffu, dg, s);
+              if (staged) {
+                const int32_t *sc = stage->col[buf] - e0;
+                const T *sv = stage->val[buf] - e0;
+  #pragma unroll 4
+                for (int q = pb; q < pe; ++q) {
+                  if ((X[sc[q]] >> lane) & 1u) hk = det::add(hk, sv[q]);
+                }
+              } else {
+                for (int q = pb; q < pe; ++q) {
+                  const int c = __ldg(p.col + q);
+                  const T v = __ldg(p.val + q);
+                  if ((X[c] >> lane) & 1u) hk = det::add(hk, v);
+                }
               }
-            } else {
-              for (int q = pb; q < pe; ++q) {
-                const int c = __ldg(p.col + q);
-                const T v = __ldg(p.val + q);
-                if ((X[c] >> lane) & 1u) hk = det::add(hk, v);
+              const uint32_t xiw = X[i];
+              const T dE = ((xiw >> lane) & 1u) ? -hk : hk;
+              const bool acc = tv && (dE < theta);
+              const bool overflow = acc ? track(i, dE) : false;
+              const uint32_t spill = __ballot_sync(0xffffffffu, overflow);
+              if (spill) {
+                materialize(spill, true);
+                if (overflow) mat = true;
               }
-            }
-            const uint32_t xiw = X[i];
-            const T dE = ((xiw >> lane) & 1u) ? -hk : hk;
-            const bool acc = tv && (dE < theta);
-            const bool overflow = acc ? track(i, dE) : false;
-            const uint32_t spill = __ballot_sync(0xffffffffu, overflow);
-            if (spill) {
-              materialize(spill, true);
-              if (overflow) mat = true;
-            }
-            const uint32_t bal = __ballot_sync(0xffffffffu, acc);
-            if (bal) {
-              __syncwarp();
-              if (lane == 0) X[i] = xiw ^ bal;
-              __syncwarp();
+              const uint32_t bal = __ballot_sync(0xffffffffu, acc);
+              if (bal) {
+                __syncwarp();
+                if (lane == 0) X[i] = xiw ^ bal;
+                __syncwarp();
+              }
             }
           }
           rp_lo = nrp_lo;
