@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libonesolver_b200.so")
+# OSA_LIB_PATH: A/B runs of tools/probe.py against another build of the same library
+LIB_PATH = os.environ.get("OSA_LIB_PATH") or os.path.join(_HERE, "lib", "libonesolver_b200.so")
 
 OSA_OK, OSA_ERR_INVALID, OSA_ERR_CUDA, OSA_ERR_NO_DEVICE, OSA_ERR_UNSUPPORTED, OSA_ERR_NOMEM = range(6)
 MODE_RANDOM_SITE, MODE_SEQUENTIAL_SWEEP = 0, 1

@@ -641,7 +641,7 @@ int osa_anneal(osa_problem *p, const double *beta_schedule, const osa_anneal_par
     stats->cyc_decide = h_cnt.cyc_decide;
     stats->cyc_apply = h_cnt.cyc_apply;
     stats->cyc_stage = h_cnt.cyc_stage;
-    stats->cyc_init = h_cnt.cyc_init;
+    stats->cyc_init = h_cnt.cyc_init + h_cnt.pad;  // pad: only with OSA_WS_DEBUG=8
     cudaEventElapsedTime(&stats->ms_sweep, p->ev[0], p->ev[1]);
     cudaEventElapsedTime(&stats->ms_energy, p->ev[1], p->ev[2]);
     cudaEventElapsedTime(&stats->ms_reduce, p->ev[2], p->ev[3]);

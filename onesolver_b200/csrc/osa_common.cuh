@@ -158,6 +158,11 @@ struct DenseParams {
   const T *tscale_traj;         // [num_tries]: per-trajectory threshold scale, replaces tscale[iter]
   uint32_t *final_states;       // [num_tries][nw]: spins after the last sweep (may alias init_states)
   uint32_t step_base;           // first sweep number of this launch in the STREAM_SEQ counter
+  // timing experiments only (OSA_WS_DEBUG, tools/probe.py; results are meaningless when set):
+  // 1 = the apply warps skip the row streaming (decide warps alone), 2 = the decide warps emit
+  // pseudo-random accept masks of density 0.19 instead of deciding (apply warps alone),
+  // 8 = cyc_init reports the walk iterations of decide warp 0 instead of cycles
+  int debug_flags;
 };
 
 template <typename T>

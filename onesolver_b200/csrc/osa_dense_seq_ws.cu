@@ -46,6 +46,15 @@ struct WsRegs {
 };
 static_assert(WsRegs<4>::APPLY == 224 && WsRegs<8>::APPLY == 200, "register split");
 
+// SM clock, read only after `dep` is available.  A clock read placed right after bar.sync can
+// execute before the barrier has released the warp; making it depend on a shared-memory load
+// issued after the barrier gives the release time (used by the role timers below).
+__device__ __forceinline__ long long clock_after(uint32_t dep) {
+  long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "r"(dep) : "memory");
+  return t;
+}
+
 template <int THREADS>
 __device__ __forceinline__ void bar_named(int id) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(THREADS) : "memory");
@@ -66,6 +75,9 @@ __global__ void __launch_bounds__(WsRegs<DW>::THREADS, 1) k_dense_seq_ws(const D
   constexpr int V = C::V, CPT = C::CPT, CHW = C::CHW, NWP = C::NWP;
   constexpr int TPD = (R + WS_DECIDE_WARPS - 1) / WS_DECIDE_WARPS;  // trajectories per decide warp
   constexpr int TILE_VECS = 32 * 32 / V;
+  // trajectories decided together by one decide warp (register budget of the decide role: 56)
+  constexpr int IL = TPD < (sizeof(T) == 4 ? 3 : 2) ? TPD : (sizeof(T) == 4 ? 3 : 2);
+  constexpr bool ALLV = (R % WS_DECIDE_WARPS == 0) && (TPD % IL == 0);  // every slot exists
 
   extern __shared__ __align__(128) unsigned char s_ring[];  // apply warps: K rows, private slots
   __shared__ __align__(16) T s_snap[2][R][32];   // columns of block g (parity g&1) after block g-2
@@ -121,12 +133,10 @@ __global__ void __launch_bounds__(WsRegs<DW>::THREADS, 1) k_dense_seq_ws(const D
       }
     };
     unsigned long long cnt_rows = 0, cnt_init_rows = 0;
-    long long t_apply = 0, t_wait = 0, t_init = 0, t_mark = clock64();
-    auto lap = [&](long long &acc) {
-      const long long now = clock64();
-      acc += now - t_mark;
-      t_mark = now;
-    };
+    // role timers (osa_stats): cyc_init = initial fields, cyc_apply = streaming/applying rows
+    // from the release of barrier B(g) on, cyc_stage = the rest of the main loop (snapshots and
+    // waiting for the decide warps)
+    long long t_apply = 0, t_init = clock64();
 
     bar_cta();  // #0: initial spins are in s_x
     for (int b = 0; b < nblk; ++b) {
@@ -141,10 +151,10 @@ __global__ void __launch_bounds__(WsRegs<DW>::THREADS, 1) k_dense_seq_ws(const D
     }
     snapshot(0, 0);
     snapshot(nblk > 1 ? 1 : 0, 1);
-    lap(t_init);
+    t_init = clock64() - t_init;
     bar_cta();  // B(-1): snapshots of blocks 0 and 1 are ready
     bar_cta();  // B(0) : masks of block 0 are ready
-    lap(t_wait);
+    const long long t_main = clock64();
     int b = 0;
     for (long long g = 0; g < total_blocks; ++g) {
       const int par = (int)(g & 1);
@@ -154,9 +164,12 @@ __global__ void __launch_bounds__(WsRegs<DW>::THREADS, 1) k_dense_seq_ws(const D
         am[r] = s_acc[par][r];
         sm[r] = s_sign[par][r];
       }
-      const uint32_t any = apply_rows<T, NCH, R, K, TH, G>(p.qoff, s_ring, p.ld, b * 32, am, sm, h, tid);
+      const long long t0 = clock_after(am[0]);
+      if (p.debug_flags & 1) am[0] = 0u;
+      const uint32_t any = (p.debug_flags & 1) ? 0u :
+          apply_rows<T, NCH, R, K, TH, G>(p.qoff, s_ring, p.ld, b * 32, am, sm, h, tid);
       cnt_rows += (unsigned)__popc(any);
-      lap(t_apply);
+      t_apply += clock64() - t0;
       if (g + 1 < total_blocks) {
         // columns of block g+2 as they are now (after block g): consumed by the decision of g+2
         int b2 = b + 2;
@@ -164,7 +177,6 @@ __global__ void __launch_bounds__(WsRegs<DW>::THREADS, 1) k_dense_seq_ws(const D
         if (b2 >= nblk) b2 -= nblk;  // nblk == 1
         snapshot(b2, par);
         bar_cta();  // B(g+1)
-        lap(t_wait);
       }
       b = (b + 1 == nblk) ? 0 : b + 1;
     }
@@ -172,8 +184,8 @@ __global__ void __launch_bounds__(WsRegs<DW>::THREADS, 1) k_dense_seq_ws(const D
       atomicAdd(&p.counters->row_fetches, cnt_rows);
       atomicAdd(&p.counters->init_row_fetches, cnt_init_rows);
       atomicAdd(&p.counters->cyc_apply, (unsigned long long)t_apply);
-      atomicAdd(&p.counters->cyc_stage, (unsigned long long)t_wait);
-      atomicAdd(&p.counters->cyc_init, (unsigned long long)t_init);
+      atomicAdd(&p.counters->cyc_stage, (unsigned long long)(clock64() - t_main - t_apply));
+      if (!(p.debug_flags & 8)) atomicAdd(&p.counters->cyc_init, (unsigned long long)t_init);
     }
   } else {
     // =============================== DECIDE ROLE ===============================
@@ -212,15 +224,32 @@ __global__ void __launch_bounds__(WsRegs<DW>::THREADS, 1) k_dense_seq_ws(const D
       s_best[r] = 0.0;
       s_atbest[r] = 1u;
     }
-    unsigned long long cnt_acc = 0;
+    unsigned long long cnt_acc = 0, n_walk = 0;
     long long t_decide = 0;
 
     bar_cta();  // #0
     bar_cta();  // B(-1): snapshots 0 and 1 ready
 
-    // decision of block (iter, sw, b) = global block g; prev_valid: block g-1 exists
+    // decision of block (iter, sw, b) = global block g.  The trajectories of this warp are
+    // decided IL at a time, interleaved: every step below is written branch-free over the IL
+    // slots (warp-uniform selects instead of branches), so the latency chains of the slots
+    // (ballot -> ffs -> tile row from shared memory -> fma) overlap.  The walk itself only
+    // carries what the next decision needs; the energy bookkeeping of annealing.hpp:115-121
+    // (running energy, strict-< best, state at the best) is done after the walk from the
+    // per-lane dE values, in the same site order, so the sums see the same fp64 additions.
     auto decide = [&](long long g, int b, uint32_t step, T ts) {
       const int par = (int)(g & 1);
+      // cyc_decide: from the release of barrier B(g-1) to the end of the decision of block g
+      const long long t0 = clock_after(*(volatile uint32_t *)&s_atbest[0]);
+      if (p.debug_flags & 2) {  // timing experiment: masks of density 3/16, no decisions
+        if (dt < R) {
+          const U4 d = engine_draw(p.seed, batch0 + (uint64_t)dt, STREAM_SEQ, (uint32_t)g, step);
+          s_acc[par][dt] = d.x & d.y & (d.z | d.w);
+          s_sign[par][dt] = d.w;
+        }
+        t_decide += clock64() - t0;
+        return;
+      }
       const int i0 = b * 32;
       const int bp = (b == 0) ? nblk - 1 : b - 1;  // previous block (cyclic)
       // stage the two tiles: diagonal tile of block b, and rows of block bp x columns of block b
@@ -233,85 +262,164 @@ __global__ void __launch_bounds__(WsRegs<DW>::THREADS, 1) k_dense_seq_ws(const D
               p.qoff + (size_t)(bp * 32 + row) * p.ld + i0 + cv * V));
       }
       bar_decide();
+      const int site = i0 + lane;
 #pragma unroll 1
-      for (int rr = 0; rr < TPD; ++rr) {
-        const int r = dwarp + rr * WS_DECIDE_WARPS;
-        if (r < R) {
-          const bool tv = r < nvalid;
-          const uint64_t traj = p.first_try + batch0 + (uint64_t)r;
-          const int site = i0 + lane;
-          T hl = s_snap[par][r][lane];
-          if (g > 0) {
-            // bring the snapshot up to date: rows of block g-1 that this trajectory flipped
-            uint32_t pa = s_acc[par ^ 1][r];
-            const uint32_t ps = s_sign[par ^ 1][r];
-            while (pa) {
-              const int s = __ffs(pa) - 1;
-              pa &= pa - 1;
-              const T sgn = ((ps >> s) & 1u) ? (T)-1 : (T)1;
-              hl = det::fma(sgn, s_tile_x[s][lane], hl);
+      for (int c0 = 0; c0 < TPD; c0 += IL) {
+        int rj[IL];       // trajectory slot of the CTA
+        bool vj[IL];      // slot exists in this CTA (R not a multiple of the interleave)
+        bool okj[IL];     // this lane may flip: trajectory exists in the batch and site < n
+        T hl[IL], theta[IL], myd[IL];
+        uint32_t xw[IL], acc[IL], from[IL];
+#pragma unroll
+        for (int j = 0; j < IL; ++j) {
+          const int r = dwarp + (c0 + j) * WS_DECIDE_WARPS;
+          vj[j] = ALLV || ((c0 + j < TPD) && (r < R));
+          rj[j] = vj[j] ? r : dwarp;
+          okj[j] = vj[j] && (rj[j] < nvalid) && (site < n);
+          hl[j] = s_snap[par][rj[j]][lane];
+          xw[j] = s_x[rj[j]][b];
+          acc[j] = 0u;
+          from[j] = 0xffffffffu;
+          myd[j] = (T)0;
+        }
+        if (g > 0) {
+          // bring the snapshots up to date: rows of block g-1 that the trajectory flipped
+          uint32_t pa[IL], ps[IL], left = 0u;
+#pragma unroll
+          for (int j = 0; j < IL; ++j) {
+            pa[j] = vj[j] ? s_acc[par ^ 1][rj[j]] : 0u;
+            ps[j] = s_sign[par ^ 1][rj[j]];
+            left |= pa[j];
+          }
+          while (left) {
+            left = 0u;
+#pragma unroll
+            for (int j = 0; j < IL; ++j) {
+              const bool on = pa[j] != 0u;
+              const int s = on ? __ffs(pa[j]) - 1 : 0;
+              pa[j] &= pa[j] - 1u;  // 0 stays 0
+              const T sgn = ((ps[j] >> s) & 1u) ? (T)-1 : (T)1;
+              const T up = det::fma(sgn, s_tile_x[s][lane], hl[j]);
+              hl[j] = on ? up : hl[j];
+              left |= pa[j];
             }
           }
-          uint32_t xw = s_x[r][b];
+        }
+#pragma unroll
+        for (int j = 0; j < IL; ++j) {
+          const uint64_t traj = p.first_try + batch0 + (uint64_t)rj[j];
           const U4 d = engine_draw(p.seed, traj, STREAM_SEQ, (uint32_t)site >> 2, step);
-          const T theta = threshold<T>(PT ? s_ts[r] : ts, pick(d, (uint32_t)site & 3u));
-          const bool lane_ok = tv && site < n;
-          uint32_t acc = 0, sg = 0, from = 0xffffffffu;
-          double erel = s_erel[r], best = s_best[r];
-          bool at_best = s_atbest[r] != 0u;
-          for (;;) {
-            const uint32_t xl = (xw >> lane) & 1u;
-            const T dEl = xl ? -hl : hl;
-            const uint32_t bal = __ballot_sync(0xffffffffu, lane_ok && (dEl < theta)) & from;
-            if (bal == 0) break;
-            const int s = __ffs(bal) - 1;
-            const T dEs = __shfl_sync(0xffffffffu, dEl, s);
-            const uint32_t xbit = (xw >> s) & 1u;
+          theta[j] = threshold<T>(PT ? s_ts[rj[j]] : ts, pick(d, (uint32_t)site & 3u));
+        }
+        // the walk: from accepted flip to accepted flip
+        for (;;) {
+          ++n_walk;
+          uint32_t bal[IL], anyb = 0u;
+          T dE[IL];
+#pragma unroll
+          for (int j = 0; j < IL; ++j) {
+            const uint32_t xl = (xw[j] >> lane) & 1u;
+            dE[j] = xl ? -hl[j] : hl[j];
+            bal[j] = __ballot_sync(0xffffffffu, okj[j] && (dE[j] < theta[j])) & from[j];
+            anyb |= bal[j];
+          }
+          if (anyb == 0u) break;
+#pragma unroll
+          for (int j = 0; j < IL; ++j) {
+            const bool on = bal[j] != 0u;
+            const int s = on ? __ffs(bal[j]) - 1 : 0;
+            const uint32_t bit = on ? (1u << s) : 0u;
+            const uint32_t xbit = (xw[j] >> s) & 1u;
             const T sgn = xbit ? (T)-1 : (T)1;
-            hl = det::fma(sgn, s_tile_d[s][lane], hl);
-            const double e = det::add(erel, (double)dEs);
-            erel = e;
-            if (e < best) {
-              best = e;
-              at_best = true;
-            } else if (at_best) {
-              // leaving the best state: snapshot the state as it was BEFORE this flip
-              for (int k = lane; k < nblk; k += 32) s_xb[r][k] = s_x[r][k];
-              __syncwarp();
-              if (lane == 0) s_xb[r][b] = xw;
-              __syncwarp();
+            const T up = det::fma(sgn, s_tile_d[s][lane], hl[j]);
+            hl[j] = on ? up : hl[j];
+            myd[j] = (on && lane == s) ? dE[j] : myd[j];
+            xw[j] ^= bit;
+            acc[j] |= bit;
+            from[j] = on ? (0xfffffffeu << s) : from[j];
+          }
+        }
+        // energies along the walk (all lanes run the same additions): erel += dE in site order,
+        // kb = site of the last flip that set a new best
+        double erel[IL], best[IL];
+        int kb[IL];
+        uint32_t rem[IL], left = 0u;
+#pragma unroll
+        for (int j = 0; j < IL; ++j) {
+          erel[j] = s_erel[rj[j]];
+          best[j] = s_best[rj[j]];
+          kb[j] = -1;
+          rem[j] = acc[j];
+          left |= rem[j];
+        }
+        while (left) {
+          left = 0u;
+#pragma unroll
+          for (int j = 0; j < IL; ++j) {
+            const bool on = rem[j] != 0u;
+            const int s = on ? __ffs(rem[j]) - 1 : 0;
+            rem[j] &= rem[j] - 1u;
+            const T dEs = __shfl_sync(0xffffffffu, myd[j], s);
+            const double e = det::add(erel[j], (double)dEs);
+            erel[j] = on ? e : erel[j];
+            const bool nb = on && (e < best[j]);
+            best[j] = nb ? e : best[j];
+            kb[j] = nb ? s : kb[j];
+            left |= rem[j];
+          }
+        }
+        // state at the best (annealing.hpp:115-121, kept lazily: s_xb is only written when the
+        // walk has left the best state by the end of the block)
+#pragma unroll
+        for (int j = 0; j < IL; ++j) {
+          if (vj[j]) {
+            const int r = rj[j];
+            // a site flips at most once per block: the word before the block and the spins
+            // that were 1 before their flip (sign -1) follow from the final word
+            const uint32_t xw0 = xw[j] ^ acc[j];
+            const uint32_t sg = acc[j] & xw0;
+            bool at_best = s_atbest[r] != 0u;
+            uint32_t wb = xw0;
+            bool copy = false;
+            if (kb[j] >= 0) {
+              const uint32_t le = (2u << kb[j]) - 1u;  // flips up to and including the best one
+              at_best = (acc[j] & ~le) == 0u;
+              copy = !at_best;
+              wb = xw0 ^ (acc[j] & le);
+            } else if (at_best && acc[j] != 0u) {
+              copy = true;  // the first flip of the block left the best state
               at_best = false;
             }
-            xw ^= (1u << s);
-            acc |= (1u << s);
-            sg |= (xbit << s);
-            from = (s == 31) ? 0u : (0xffffffffu << (s + 1));
-          }
-          if (lane == 0) {
-            s_erel[r] = erel;
-            s_best[r] = best;
-            s_atbest[r] = at_best ? 1u : 0u;
-            s_x[r][b] = xw;
-            s_acc[par][r] = acc;
-            s_sign[par][r] = sg;
-            cnt_acc += (unsigned)__popc(acc);
+            if (copy) {
+              for (int k = lane; k < nblk; k += 32) s_xb[r][k] = s_x[r][k];
+              __syncwarp();
+              if (lane == 0) s_xb[r][b] = wb;
+            }
+            __syncwarp();
+            if (lane == 0) {
+              s_erel[r] = erel[j];
+              s_best[r] = best[j];
+              s_atbest[r] = at_best ? 1u : 0u;
+              s_x[r][b] = xw[j];
+              s_acc[par][r] = acc[j];
+              s_sign[par][r] = sg;
+              cnt_acc += (unsigned)__popc(acc[j]);
+            }
           }
         }
       }
       bar_decide();  // the tiles may be overwritten by the next call
+      t_decide += clock64() - t0;
     };
 
     long long g = 0;
     uint32_t step = PT ? p.step_base : 0u;
-    long long t_mark = clock64();
     for (int iter = 0; iter < p.num_iter; ++iter) {
       const T ts = PT ? (T)0 : p.tscale[iter];
       for (int sw = 0; sw < p.sweeps_per_beta; ++sw, ++step) {
         for (int b = 0; b < nblk; ++b, ++g) {
           decide(g, b, step, ts);
-          t_decide += clock64() - t_mark;
           bar_cta();  // B(g): masks of block g ready (g = 0: the apply warps have been waiting)
-          t_mark = clock64();
         }
       }
     }
@@ -334,6 +442,7 @@ __global__ void __launch_bounds__(WsRegs<DW>::THREADS, 1) k_dense_seq_ws(const D
     if (lane == 0) {
       if (cnt_acc) atomicAdd(&p.counters->accepts, cnt_acc);
       if (dwarp == 0) atomicAdd(&p.counters->cyc_decide, (unsigned long long)t_decide);
+      if (dwarp == 0 && (p.debug_flags & 8)) atomicAdd(&p.counters->pad, n_walk);
     }
   }
 }
@@ -347,9 +456,12 @@ cudaError_t launch_ws(const DenseParams<T> &p, cudaStream_t s, LaunchInfo *info)
   // the resumable instantiation only when a per-trajectory scale is given (osa_pt_anneal)
   auto kern = p.tscale_traj ? k_dense_seq_ws<T, NCH, R, K, G, true, DW>
                             : k_dense_seq_ws<T, NCH, R, K, G, false, DW>;
+  DenseParams<T> pd = p;
+  const char *dbg = getenv("OSA_WS_DEBUG");  // timing experiments, see DenseParams::debug_flags
+  pd.debug_flags = dbg ? atoi(dbg) : 0;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
-  kern<<<(unsigned)grid64, WS_THREADS, smem, s>>>(p);
+  kern<<<(unsigned)grid64, WS_THREADS, smem, s>>>(pd);
   if (info) {
     info->grid = (int)grid64;
     info->block = WS_THREADS;

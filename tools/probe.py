@@ -65,6 +65,18 @@ if "dense" in what:
     run_dense(512, capi.SWEEP_F64, 148 * 16, 16, 0.3 * s, 0.02 * s, "dense512_f64")
     run_dense(4096, capi.SWEEP_F64, 148 * 4, 2, 0.3 * 64, 0.02 * 64, "dense4096_f64")
 
+if "dbg" in what:
+    # role experiments of the warp-specialised kernel (DenseParams::debug_flags): 8 = normal run,
+    # cyc_init = walk iterations of decide warp 0; 9 = decide warps alone; 2 = apply warps alone
+    import os
+    s = np.sqrt(4096)
+    for flags in ("8", "9", "2"):
+        os.environ["OSA_WS_DEBUG"] = flags
+        run_dense(4096, capi.SWEEP_F32, 148 * 12, 4, 0.3 * s, 0.02 * s, "dbg%s_4096_hot2cold" % flags)
+        run_dense(4096, capi.SWEEP_F32, 148 * 12, 4, 0.01 * s, 0.002 * s, "dbg%s_4096_cold" % flags)
+        run_dense(1024, capi.SWEEP_F64, 148 * 16, 8, 0.3 * 32, 0.02 * 32, "dbg%s_1024_f64" % flags)
+    os.environ.pop("OSA_WS_DEBUG")
+
 if "cfg" in what:
     import os
     s = np.sqrt(4096)
