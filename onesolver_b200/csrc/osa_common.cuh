@@ -161,7 +161,8 @@ struct DenseParams {
   // timing experiments only (OSA_WS_DEBUG, tools/probe.py; results are meaningless when set):
   // 1 = the apply warps skip the row streaming (decide warps alone), 2 = the decide warps emit
   // pseudo-random accept masks of density 0.19 instead of deciding (apply warps alone),
-  // 8 = cyc_init reports the walk iterations of decide warp 0 instead of cycles
+  // 8 = cyc_init / cyc_stage report two phases of the walker warp (bringing the snapshot up to
+  // date, walking the sites) instead of the apply-role timers
   int debug_flags;
 };
 

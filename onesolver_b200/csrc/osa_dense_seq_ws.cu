@@ -60,38 +60,101 @@ __device__ __forceinline__ void bar_named(int id) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(THREADS) : "memory");
 }
 
+// HS consecutive elements from a (HS * sizeof(T))-byte aligned shared-memory address
+template <typename T, int HS>
+__device__ __forceinline__ void load_seg(const T *src, T (&out)[HS]) {
+  constexpr int BYTES = HS * (int)sizeof(T);
+  if constexpr (BYTES % 16 == 0) {
+    constexpr int V = 16 / (int)sizeof(T);
+#pragma unroll
+    for (int i = 0; i < HS; i += V)
+      vec_unpack<T>(*reinterpret_cast<const typename Vec16<T>::type *>(src + i), &out[i]);
+  } else if constexpr (BYTES == 8 && sizeof(T) == 4) {
+    const float2 v = *reinterpret_cast<const float2 *>(src);
+    out[0] = v.x;
+    out[1] = v.y;
+  } else {
+#pragma unroll
+    for (int i = 0; i < HS; ++i) out[i] = src[i];
+  }
+}
+
+// Shared memory of the CTA next to the row ring, as structs, so that the launcher can size the
+// ring (K rows) from what is left of the 227 KiB.  WsTiles follows the ring in dynamic shared
+// memory (statically allocated shared memory is limited to 48 KiB).
+template <typename T>
+struct WsTiles {
+  static constexpr int TP = 32 + 16 / (int)sizeof(T);  // tile row pitch: 16-byte aligned rows whose
+                                                       // 16-byte chunks rotate through the banks
+  alignas(16) T tile_d[2][32][TP];  // diagonal tile of block j (parity j&1)
+  alignas(16) T tile_x[2][32][TP];  // rows of block j-1 x columns of block j
+};
+
+template <typename T, int R, int NWP>
+struct WsShared {
+  alignas(16) T snap[2][32][R];     // columns of block j (parity j&1) after block j-2, [column][traj]
+  alignas(16) T theta[2][32][R];    // acceptance thresholds of block j, [site][traj]
+  T dE[32][R];                      // dE of the accepted flips of the block being decided
+  double erel[R], best[R];          // running / best energy relative to the start
+  T ts[R];                          // per-trajectory threshold scale (only with p.tscale_traj)
+  uint32_t atbest[R];
+  uint32_t naccept[R];              // accepted flips (32-bit; flushed to the 64-bit counter)
+  uint32_t x[NWP][R];               // current spins, [word][traj]
+};
+
+constexpr int WS_SMEM_LIMIT = 232448 - 1024 - 256;  // 227 KiB minus the per-CTA reservation
+
+template <typename T, int NCH, int R, int K>
+struct WsRing {
+  using C = Cfg<T, NCH, R, WS_APPLY_THREADS>;
+  static constexpr int ROW_BYTES = NCH * WS_APPLY_THREADS * 16;
+  static constexpr int FIT =
+      (WS_SMEM_LIMIT - (int)sizeof(WsShared<T, R, C::NWP>) - 16 * R - (int)sizeof(WsTiles<T>)) / ROW_BYTES;
+  static constexpr int KE = K < FIT ? K : FIT;  // rows in flight
+  static_assert(KE >= 3, "row ring too small");
+};
+
 // PT: resumable launch for parallel tempering (start spins from memory, per-trajectory threshold
 // scale, final spins written back, running sweep counter); a separate instantiation so that the
 // plain annealing kernel carries none of it.
+//
+// Decide role.  Every decide warp walks R/DW trajectories of the CTA side by side: NSEG lanes per
+// trajectory, each holding the local fields of HS = 32/NSEG sites of the block in registers
+// (R = 12, DW = 4: three trajectories x eight lanes x four sites).  The sites are walked in order
+// -- compare, and on an accepted flip add the row of the diagonal tile to the fields of the later
+// sites, under a per-lane predicate; the lanes of the later segments learn the decision through a
+// ballot.  The cost does not depend on how many flips are accepted, and everything around the
+// walk (bringing the snapshot up to date, the energy bookkeeping) is branch-free over the 32
+// sites so that its shared-memory loads run ahead of the arithmetic.  After its walk a warp helps
+// to prepare the next block: Philox draws and thresholds of all (site, trajectory) pairs and the
+// two tiles of Q (cp.async), into the other half of double buffers; the CTA barrier that ends
+// the block publishes them.
 template <typename T, int NCH, int R, int K, int G, bool PT, int DW>
 __global__ void __launch_bounds__(WsRegs<DW>::THREADS, 1) k_dense_seq_ws(const DenseParams<T> p) {
   constexpr int TH = WS_APPLY_THREADS;
-  constexpr int WS_DECIDE_WARPS = DW;
   constexpr int WS_THREADS = WsRegs<DW>::THREADS;
   auto bar_cta = [] { bar_named<WS_THREADS>(1); };
-  auto bar_decide = [] { bar_named<DW * 32>(2); };
   using C = Cfg<T, NCH, R, TH>;
   using VecT = typename C::VecT;
   constexpr int V = C::V, CPT = C::CPT, CHW = C::CHW, NWP = C::NWP;
-  constexpr int TPD = (R + WS_DECIDE_WARPS - 1) / WS_DECIDE_WARPS;  // trajectories per decide warp
+  constexpr int KE = WsRing<T, NCH, R, K>::KE;
   constexpr int TILE_VECS = 32 * 32 / V;
-  // trajectories decided together by one decide warp (register budget of the decide role: 56)
-  constexpr int IL = TPD < (sizeof(T) == 4 ? 3 : 2) ? TPD : (sizeof(T) == 4 ? 3 : 2);
-  constexpr bool ALLV = (R % WS_DECIDE_WARPS == 0) && (TPD % IL == 0);  // every slot exists
+  constexpr int DT = DW * 32;         // threads of the decide role
+  // every decide warp walks TPW trajectories, NSEG lanes per trajectory, each lane with the
+  // fields of HS sites in registers
+  constexpr int TPW = (R + DW - 1) / DW;
+  constexpr int NSEG = TPW <= 1 ? 32 : TPW <= 2 ? 16 : TPW <= 4 ? 8 : TPW <= 8 ? 4 : 2;
+  constexpr int HS = 32 / NSEG;
+  static_assert(TPW * NSEG <= 32, "lanes of a decide warp");
 
-  extern __shared__ __align__(128) unsigned char s_ring[];  // apply warps: K rows, private slots
-  __shared__ __align__(16) T s_snap[2][R][32];   // columns of block g (parity g&1) after block g-2
-  __shared__ __align__(16) T s_tile_d[32][32];   // diagonal tile of the block being decided
-  __shared__ __align__(16) T s_tile_x[32][32];   // rows of the previous block x columns of this one
-  __shared__ uint32_t s_acc[2][R];               // accept / sign masks of block g (parity g&1)
-  __shared__ uint32_t s_sign[2][R];
-  // per-trajectory walk state of the decide warps (indexed by a run-time trajectory number, so it
-  // lives here rather than in a register array that the compiler would demote to local memory)
-  __shared__ double s_erel[R], s_best[R];
-  __shared__ T s_ts[R];  // per-trajectory threshold scale (only with p.tscale_traj)
-  __shared__ uint32_t s_atbest[R];
-  __shared__ uint32_t s_x[R][NWP];
-  __shared__ uint32_t s_xb[R][NWP];
+  // dynamic shared memory: the row ring of the apply warps (KE rows, private slots), then WsTiles
+  extern __shared__ __align__(128) unsigned char s_ring[];
+  __shared__ WsShared<T, R, NWP> sh;
+  // accept / sign masks of block j (parity j&1).  Kept as plain arrays: the apply warps read them
+  // with scalar loads at warp-uniform addresses, which keeps the 2R masks in uniform registers
+  // through apply_rows (as members of the 16-byte aligned struct they were read with vector loads
+  // into ordinary registers, and the kernel spilled)
+  __shared__ uint32_t s_acc[2][R], s_sign[2][R];
 
   const int tid = threadIdx.x;
   const int n = p.n;
@@ -115,7 +178,7 @@ __global__ void __launch_bounds__(WsRegs<DW>::THREADS, 1) k_dense_seq_ws(const D
 #pragma unroll
         for (int e = 0; e < V; ++e) h[r].set(c * V + e, dv[e]);
     }
-    // snapshot of the 32 columns of block b into s_snap[par]
+    // snapshot of the 32 columns of block b into sh.snap[par]
     auto snapshot = [&](int b, int par) {
       const int i0 = b * 32;
       const int cb = i0 / CHW;
@@ -125,9 +188,9 @@ __global__ void __launch_bounds__(WsRegs<DW>::THREADS, 1) k_dense_seq_ws(const D
         for (int c = 0; c < NCH; ++c) {
           if (c == cb) {
 #pragma unroll
-            for (int r = 0; r < R; ++r)
+            for (int e = 0; e < V; ++e)
 #pragma unroll
-              for (int e = 0; e < V; ++e) s_snap[par][r][rel + e] = h[r].get(c * V + e);
+              for (int r = 0; r < R; ++r) sh.snap[par][rel + e][r] = h[r].get(c * V + e);
           }
         }
       }
@@ -138,15 +201,15 @@ __global__ void __launch_bounds__(WsRegs<DW>::THREADS, 1) k_dense_seq_ws(const D
     // waiting for the decide warps)
     long long t_apply = 0, t_init = clock64();
 
-    bar_cta();  // #0: initial spins are in s_x
+    bar_cta();  // #0: initial spins are in sh.x
     for (int b = 0; b < nblk; ++b) {
       uint32_t am[R], sm[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        am[r] = s_x[r][b];
+        am[r] = sh.x[b][r];
         sm[r] = 0u;
       }
-      const uint32_t any = apply_rows<T, NCH, R, K, TH, G>(p.qoff, s_ring, p.ld, b * 32, am, sm, h, tid);
+      const uint32_t any = apply_rows<T, NCH, R, KE, TH, G>(p.qoff, s_ring, p.ld, b * 32, am, sm, h, tid);
       cnt_init_rows += (unsigned)__popc(any);
     }
     snapshot(0, 0);
@@ -167,7 +230,7 @@ __global__ void __launch_bounds__(WsRegs<DW>::THREADS, 1) k_dense_seq_ws(const D
       const long long t0 = clock_after(am[0]);
       if (p.debug_flags & 1) am[0] = 0u;
       const uint32_t any = (p.debug_flags & 1) ? 0u :
-          apply_rows<T, NCH, R, K, TH, G>(p.qoff, s_ring, p.ld, b * 32, am, sm, h, tid);
+          apply_rows<T, NCH, R, KE, TH, G>(p.qoff, s_ring, p.ld, b * 32, am, sm, h, tid);
       cnt_rows += (unsigned)__popc(any);
       t_apply += clock64() - t0;
       if (g + 1 < total_blocks) {
@@ -184,265 +247,282 @@ __global__ void __launch_bounds__(WsRegs<DW>::THREADS, 1) k_dense_seq_ws(const D
       atomicAdd(&p.counters->row_fetches, cnt_rows);
       atomicAdd(&p.counters->init_row_fetches, cnt_init_rows);
       atomicAdd(&p.counters->cyc_apply, (unsigned long long)t_apply);
-      atomicAdd(&p.counters->cyc_stage, (unsigned long long)(clock64() - t_main - t_apply));
-      if (!(p.debug_flags & 8)) atomicAdd(&p.counters->cyc_init, (unsigned long long)t_init);
+      if (!(p.debug_flags & 8)) {
+        atomicAdd(&p.counters->cyc_stage, (unsigned long long)(clock64() - t_main - t_apply));
+        atomicAdd(&p.counters->cyc_init, (unsigned long long)t_init);
+      }
     }
   } else {
     // =============================== DECIDE ROLE ===============================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WsRegs<DW>::DECIDE));
-    const int dt = tid - WS_APPLY_THREADS;  // 0..127
+    const int dt = tid - WS_APPLY_THREADS;
     const int lane = dt & 31, dwarp = dt >> 5;
+    WsTiles<T> &tl = *reinterpret_cast<WsTiles<T> *>(s_ring + (size_t)KE * WsRing<T, NCH, R, K>::ROW_BYTES);
 
     // initial spins (replaces random.bit(), annealing.hpp:90-92)
-#pragma unroll 1
-    for (int rr = 0; rr < TPD; ++rr) {
-      const int r = dwarp + rr * WS_DECIDE_WARPS;
-      if (r < R) {
-        const bool tv = r < nvalid;
-        const uint64_t traj = p.first_try + batch0 + (uint64_t)r;
-        for (int k = lane; k < NWP; k += 32) {
-          uint32_t word = 0;
-          if (tv && k < nblk) {
-            if (PT && p.init_states) {  // resume: the spins a previous launch left in final_states
-              word = p.init_states[(batch0 + (uint64_t)r) * (uint64_t)p.nw + k];
-            } else {
-              const U4 d = engine_draw(p.seed, traj, STREAM_INIT, (uint32_t)k >> 2, 0u);
-              word = pick(d, (uint32_t)k & 3u);
-            }
-            const int valid = n - k * 32;
-            if (valid < 32) word &= (1u << valid) - 1u;
-          }
-          s_x[r][k] = word;
-          s_xb[r][k] = word;
+    for (int q = dt; q < R * NWP; q += DT) {
+      const int r = q / NWP, k = q % NWP;
+      uint32_t word = 0;
+      if (r < nvalid && k < nblk) {
+        if (PT && p.init_states) {  // resume: the spins a previous launch left in final_states
+          word = p.init_states[(batch0 + (uint64_t)r) * (uint64_t)p.nw + k];
+        } else {
+          const U4 d = engine_draw(p.seed, p.first_try + batch0 + (uint64_t)r, STREAM_INIT,
+                                   (uint32_t)k >> 2, 0u);
+          word = pick(d, (uint32_t)k & 3u);
         }
-        if (PT && lane == 0)
-          s_ts[r] = (p.tscale_traj && tv) ? p.tscale_traj[batch0 + (uint64_t)r] : (T)0;
+        const int valid = n - k * 32;
+        if (valid < 32) word &= (1u << valid) - 1u;
       }
+      sh.x[k][r] = word;
     }
-    for (int r = dt; r < R; r += WS_DECIDE_WARPS * 32) {
-      s_erel[r] = 0.0;
-      s_best[r] = 0.0;
-      s_atbest[r] = 1u;
+    for (int r = dt; r < R; r += DT) {
+      sh.erel[r] = 0.0;
+      sh.best[r] = 0.0;
+      sh.atbest[r] = 1u;
+      sh.naccept[r] = 0u;
+      sh.ts[r] = (PT && p.tscale_traj && r < nvalid) ? p.tscale_traj[batch0 + (uint64_t)r] : (T)0;
     }
-    unsigned long long cnt_acc = 0, n_walk = 0;
-    long long t_decide = 0;
 
-    bar_cta();  // #0
-    bar_cta();  // B(-1): snapshots 0 and 1 ready
-
-    // decision of block (iter, sw, b) = global block g.  The trajectories of this warp are
-    // decided IL at a time, interleaved: every step below is written branch-free over the IL
-    // slots (warp-uniform selects instead of branches), so the latency chains of the slots
-    // (ballot -> ffs -> tile row from shared memory -> fma) overlap.  The walk itself only
-    // carries what the next decision needs; the energy bookkeeping of annealing.hpp:115-121
-    // (running energy, strict-< best, state at the best) is done after the walk from the
-    // per-lane dE values, in the same site order, so the sums see the same fp64 additions.
-    auto decide = [&](long long g, int b, uint32_t step, T ts) {
-      const int par = (int)(g & 1);
-      // cyc_decide: from the release of barrier B(g-1) to the end of the decision of block g
-      const long long t0 = clock_after(*(volatile uint32_t *)&s_atbest[0]);
-      if (p.debug_flags & 2) {  // timing experiment: masks of density 3/16, no decisions
-        if (dt < R) {
-          const U4 d = engine_draw(p.seed, batch0 + (uint64_t)dt, STREAM_SEQ, (uint32_t)g, step);
-          s_acc[par][dt] = d.x & d.y & (d.z | d.w);
-          s_sign[par][dt] = d.w;
-        }
-        t_decide += clock64() - t0;
-        return;
-      }
-      const int i0 = b * 32;
-      const int bp = (b == 0) ? nblk - 1 : b - 1;  // previous block (cyclic)
-      // stage the two tiles: diagonal tile of block b, and rows of block bp x columns of block b
-      for (int qi = dt; qi < TILE_VECS; qi += WS_DECIDE_WARPS * 32) {
-        const int row = qi / (32 / V), cv = qi % (32 / V);
-        *reinterpret_cast<VecT *>(&s_tile_d[row][cv * V]) =
-            __ldg(reinterpret_cast<const VecT *>(p.qoff + (size_t)(i0 + row) * p.ld + i0 + cv * V));
-        if (g > 0)
-          *reinterpret_cast<VecT *>(&s_tile_x[row][cv * V]) = __ldg(reinterpret_cast<const VecT *>(
-              p.qoff + (size_t)(bp * 32 + row) * p.ld + i0 + cv * V));
-      }
-      bar_decide();
-      const int site = i0 + lane;
-#pragma unroll 1
-      for (int c0 = 0; c0 < TPD; c0 += IL) {
-        int rj[IL];       // trajectory slot of the CTA
-        bool vj[IL];      // slot exists in this CTA (R not a multiple of the interleave)
-        bool okj[IL];     // this lane may flip: trajectory exists in the batch and site < n
-        T hl[IL], theta[IL], myd[IL];
-        uint32_t xw[IL], acc[IL], from[IL];
-#pragma unroll
-        for (int j = 0; j < IL; ++j) {
-          const int r = dwarp + (c0 + j) * WS_DECIDE_WARPS;
-          vj[j] = ALLV || ((c0 + j < TPD) && (r < R));
-          rj[j] = vj[j] ? r : dwarp;
-          okj[j] = vj[j] && (rj[j] < nvalid) && (site < n);
-          hl[j] = s_snap[par][rj[j]][lane];
-          xw[j] = s_x[rj[j]][b];
-          acc[j] = 0u;
-          from[j] = 0xffffffffu;
-          myd[j] = (T)0;
-        }
-        if (g > 0) {
-          // bring the snapshots up to date: rows of block g-1 that the trajectory flipped
-          uint32_t pa[IL], ps[IL], left = 0u;
-#pragma unroll
-          for (int j = 0; j < IL; ++j) {
-            pa[j] = vj[j] ? s_acc[par ^ 1][rj[j]] : 0u;
-            ps[j] = s_sign[par ^ 1][rj[j]];
-            left |= pa[j];
-          }
-          while (left) {
-            left = 0u;
-#pragma unroll
-            for (int j = 0; j < IL; ++j) {
-              const bool on = pa[j] != 0u;
-              const int s = on ? __ffs(pa[j]) - 1 : 0;
-              pa[j] &= pa[j] - 1u;  // 0 stays 0
-              const T sgn = ((ps[j] >> s) & 1u) ? (T)-1 : (T)1;
-              const T up = det::fma(sgn, s_tile_x[s][lane], hl[j]);
-              hl[j] = on ? up : hl[j];
-              left |= pa[j];
-            }
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < IL; ++j) {
-          const uint64_t traj = p.first_try + batch0 + (uint64_t)rj[j];
-          const U4 d = engine_draw(p.seed, traj, STREAM_SEQ, (uint32_t)site >> 2, step);
-          theta[j] = threshold<T>(PT ? s_ts[rj[j]] : ts, pick(d, (uint32_t)site & 3u));
-        }
-        // the walk: from accepted flip to accepted flip
-        for (;;) {
-          ++n_walk;
-          uint32_t bal[IL], anyb = 0u;
-          T dE[IL];
-#pragma unroll
-          for (int j = 0; j < IL; ++j) {
-            const uint32_t xl = (xw[j] >> lane) & 1u;
-            dE[j] = xl ? -hl[j] : hl[j];
-            bal[j] = __ballot_sync(0xffffffffu, okj[j] && (dE[j] < theta[j])) & from[j];
-            anyb |= bal[j];
-          }
-          if (anyb == 0u) break;
-#pragma unroll
-          for (int j = 0; j < IL; ++j) {
-            const bool on = bal[j] != 0u;
-            const int s = on ? __ffs(bal[j]) - 1 : 0;
-            const uint32_t bit = on ? (1u << s) : 0u;
-            const uint32_t xbit = (xw[j] >> s) & 1u;
-            const T sgn = xbit ? (T)-1 : (T)1;
-            const T up = det::fma(sgn, s_tile_d[s][lane], hl[j]);
-            hl[j] = on ? up : hl[j];
-            myd[j] = (on && lane == s) ? dE[j] : myd[j];
-            xw[j] ^= bit;
-            acc[j] |= bit;
-            from[j] = on ? (0xfffffffeu << s) : from[j];
-          }
-        }
-        // energies along the walk (all lanes run the same additions): erel += dE in site order,
-        // kb = site of the last flip that set a new best
-        double erel[IL], best[IL];
-        int kb[IL];
-        uint32_t rem[IL], left = 0u;
-#pragma unroll
-        for (int j = 0; j < IL; ++j) {
-          erel[j] = s_erel[rj[j]];
-          best[j] = s_best[rj[j]];
-          kb[j] = -1;
-          rem[j] = acc[j];
-          left |= rem[j];
-        }
-        while (left) {
-          left = 0u;
-#pragma unroll
-          for (int j = 0; j < IL; ++j) {
-            const bool on = rem[j] != 0u;
-            const int s = on ? __ffs(rem[j]) - 1 : 0;
-            rem[j] &= rem[j] - 1u;
-            const T dEs = __shfl_sync(0xffffffffu, myd[j], s);
-            const double e = det::add(erel[j], (double)dEs);
-            erel[j] = on ? e : erel[j];
-            const bool nb = on && (e < best[j]);
-            best[j] = nb ? e : best[j];
-            kb[j] = nb ? s : kb[j];
-            left |= rem[j];
-          }
-        }
-        // state at the best (annealing.hpp:115-121, kept lazily: s_xb is only written when the
-        // walk has left the best state by the end of the block)
-#pragma unroll
-        for (int j = 0; j < IL; ++j) {
-          if (vj[j]) {
-            const int r = rj[j];
-            // a site flips at most once per block: the word before the block and the spins
-            // that were 1 before their flip (sign -1) follow from the final word
-            const uint32_t xw0 = xw[j] ^ acc[j];
-            const uint32_t sg = acc[j] & xw0;
-            bool at_best = s_atbest[r] != 0u;
-            uint32_t wb = xw0;
-            bool copy = false;
-            if (kb[j] >= 0) {
-              const uint32_t le = (2u << kb[j]) - 1u;  // flips up to and including the best one
-              at_best = (acc[j] & ~le) == 0u;
-              copy = !at_best;
-              wb = xw0 ^ (acc[j] & le);
-            } else if (at_best && acc[j] != 0u) {
-              copy = true;  // the first flip of the block left the best state
-              at_best = false;
-            }
-            if (copy) {
-              for (int k = lane; k < nblk; k += 32) s_xb[r][k] = s_x[r][k];
-              __syncwarp();
-              if (lane == 0) s_xb[r][b] = wb;
-            }
-            __syncwarp();
-            if (lane == 0) {
-              s_erel[r] = erel[j];
-              s_best[r] = best[j];
-              s_atbest[r] = at_best ? 1u : 0u;
-              s_x[r][b] = xw[j];
-              s_acc[par][r] = acc[j];
-              s_sign[par][r] = sg;
-              cnt_acc += (unsigned)__popc(acc[j]);
-            }
-          }
+    // position of a block in the schedule
+    struct BlockIt {
+      int iter, sw, b;
+      uint32_t step;
+    };
+    auto advance = [&](BlockIt &c) {
+      if (++c.b == nblk) {
+        c.b = 0;
+        ++c.step;
+        if (++c.sw == p.sweeps_per_beta) {
+          c.sw = 0;
+          ++c.iter;
         }
       }
-      bar_decide();  // the tiles may be overwritten by the next call
-      t_decide += clock64() - t0;
     };
 
-    long long g = 0;
-    uint32_t step = PT ? p.step_base : 0u;
-    for (int iter = 0; iter < p.num_iter; ++iter) {
-      const T ts = PT ? (T)0 : p.tscale[iter];
-      for (int sw = 0; sw < p.sweeps_per_beta; ++sw, ++step) {
-        for (int b = 0; b < nblk; ++b, ++g) {
-          decide(g, b, step, ts);
-          bar_cta();  // B(g): masks of block g ready (g = 0: the apply warps have been waiting)
+    // thresholds and tiles of block c into the buffers of parity `buf` (all decide threads).  The
+    // tiles go straight from L2 to shared memory (cp.async) while the thresholds are computed.
+    auto prepare = [&](const BlockIt &c, int buf) {
+      const int i0 = c.b * 32;
+      const int bp = (c.b == 0) ? nblk - 1 : c.b - 1;  // previous block (cyclic)
+      for (int qi = dt; qi < TILE_VECS; qi += DT) {
+        const int row = qi / (32 / V), cv = qi % (32 / V);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(&tl.tile_d[buf][row][cv * V])),
+                     "l"(p.qoff + (size_t)(i0 + row) * p.ld + i0 + cv * V)
+                     : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(&tl.tile_x[buf][row][cv * V])),
+                     "l"(p.qoff + (size_t)(bp * 32 + row) * p.ld + i0 + cv * V)
+                     : "memory");
+      }
+      // one Philox block serves four consecutive sites of a trajectory (STREAM_SEQ: c0 = site>>2)
+      const T ts = PT ? (T)0 : p.tscale[c.iter];
+      for (int q = dt; q < R * 8; q += DT) {
+        const int r = q >> 3, grp = q & 7;
+        const uint64_t traj = p.first_try + batch0 + (uint64_t)r;
+        const U4 d = engine_draw(p.seed, traj, STREAM_SEQ, (uint32_t)(i0 >> 2) + grp, c.step);
+        const T tsr = PT ? sh.ts[r] : ts;
+        sh.theta[buf][grp * 4 + 0][r] = threshold<T>(tsr, d.x);
+        sh.theta[buf][grp * 4 + 1][r] = threshold<T>(tsr, d.y);
+        sh.theta[buf][grp * 4 + 2][r] = threshold<T>(tsr, d.z);
+        sh.theta[buf][grp * 4 + 3][r] = threshold<T>(tsr, d.w);
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");
+    };
+
+    // walk state: lane = (slot t of the warp's trajectories, column segment seg); the lanes of a
+    // trajectory are NSEG consecutive lanes, each with the fields of HS sites in registers
+    const int t = lane / NSEG, seg = lane % NSEG;
+    const int r = dwarp + DW * t;
+    const bool has = (t < TPW) && (r < R);
+    const int rr = has ? r : 0;
+    const bool tv = has && r < nvalid;
+    const bool lead = has && seg == 0;
+    const int c0 = seg * HS;
+    uint32_t pa = 0u, ps = 0u;  // accept / sign masks of the previous block (every lane of r)
+    long long t_decide = 0, t_catch = 0, t_sites = 0;  // the last two only with debug flag 8
+
+    // decision of block j of the schedule (block b of the sweep) for the trajectories of this warp
+    auto walk = [&](long long j, int b) {
+      const int par = (int)(j & 1);
+      const int i0 = b * 32;
+      const uint32_t xw0 = sh.x[b][rr];
+      // cyc_decide: from the release of barrier B(j-1) to the arrival at B(j)
+      const long long t0 = clock_after(xw0);
+      if (p.debug_flags & 2) {  // timing experiment: masks of density 3/16, no decisions
+        if (lead) {
+          const U4 d = engine_draw(p.seed, batch0 + (uint64_t)r, STREAM_SEQ, (uint32_t)j, 0u);
+          s_acc[par][r] = d.x & d.y & (d.z | d.w);
+          s_sign[par][r] = d.w;
         }
+        return t0;
+      }
+      long long tp = (p.debug_flags & 8) ? clock64() : 0;
+      T hs[HS];
+#pragma unroll
+      for (int k = 0; k < HS; ++k) hs[k] = sh.snap[par][c0 + k][rr];
+      // bring the snapshot up to date: the rows of block j-1 that the trajectory flipped, in site
+      // order -- the same fma sequence the apply warps run on these columns, hence the same bits.
+      // Branch-free over the 32 sites, so that the loads run ahead of the arithmetic.
+      {
+        const T(*tx)[WsTiles<T>::TP] = tl.tile_x[par];
+#pragma unroll
+        for (int s = 0; s < 32; ++s) {
+          const bool on = ((pa >> s) & 1u) != 0u;
+          const T sgn = ((ps >> s) & 1u) ? (T)-1 : (T)1;
+          T qv[HS];
+          load_seg<T, HS>(&tx[s][c0], qv);
+#pragma unroll
+          for (int k = 0; k < HS; ++k) {
+            const T up = det::fma(sgn, qv[k], hs[k]);
+            hs[k] = on ? up : hs[k];
+          }
+        }
+      }
+      if (p.debug_flags & 8) {
+        const long long now = clock_after(__float_as_uint((float)hs[0]));
+        t_catch += now - tp;
+        tp = now;
+      }
+      // the walk: phase ph decides the sites of segment ph, site by site; an accepted flip adds
+      // the row of the diagonal tile to the fields of the later sites -- in the deciding lane for
+      // its own segment, in the lanes of the later segments after a ballot
+      uint32_t acc = 0u;
+      const T(*td)[WsTiles<T>::TP] = tl.tile_d[par];
+#pragma unroll
+      for (int ph = 0; ph < NSEG; ++ph) {
+#pragma unroll
+        for (int s = 0; s < HS; ++s) {
+          const int site = ph * HS + s;
+          if (ph + 1 == NSEG && s + 1 == HS) {  // last site: nothing left to update
+            const T th = sh.theta[par][site][rr];
+            const bool xl = ((xw0 >> site) & 1u) != 0u;
+            const T dE = xl ? -hs[s] : hs[s];
+            const bool okm = tv && (seg == ph) && (i0 + site < n) && (dE < th);
+            if (okm) sh.dE[site][rr] = dE;
+            acc |= okm ? (1u << site) : 0u;
+            continue;
+          }
+          const T th = sh.theta[par][site][rr];
+          const bool xl = ((xw0 >> site) & 1u) != 0u;  // a site flips at most once per block
+          const T dE = xl ? -hs[s] : hs[s];
+          const bool okm = tv && (seg == ph) && (i0 + site < n) && (dE < th);
+          if (okm) sh.dE[site][rr] = dE;
+          bool okp = false;  // the decision of my trajectory, seen from a later segment
+          if (ph + 1 < NSEG) {
+            const uint32_t bal = __ballot_sync(0xffffffffu, okm);
+            okp = (seg > ph) && (((bal >> (t * NSEG + ph)) & 1u) != 0u);
+          }
+          const T sgn = xl ? (T)-1 : (T)1;
+          T qv[HS];
+          load_seg<T, HS>(&td[site][c0], qv);
+#pragma unroll
+          for (int k = 0; k < HS; ++k) {
+            if (k > s || ph + 1 < NSEG) {
+              const bool pr = (k > s) ? (okm || okp) : okp;
+              const T up = det::fma(sgn, qv[k], hs[k]);
+              hs[k] = pr ? up : hs[k];
+            }
+          }
+          acc |= okm ? (1u << site) : 0u;
+        }
+      }
+      // every lane of a trajectory gets the whole accept mask
+#pragma unroll
+      for (int d = 1; d < NSEG; d *= 2) acc |= __shfl_xor_sync(0xffffffffu, acc, d);
+      if (p.debug_flags & 8) t_sites += clock_after(acc) - tp;
+      // energies along the walk (annealing.hpp:115-121), in the lead lane of the trajectory:
+      // erel += dE in site order, kb = site of the last flip that set a new best (strict <)
+      double erel = sh.erel[rr], best = sh.best[rr];
+      int kb = -1;
+#pragma unroll
+      for (int s = 0; s < 32; ++s) {
+        const bool on = ((acc >> s) & 1u) != 0u;
+        const double e = det::add(erel, (double)sh.dE[s][rr]);
+        erel = on ? e : erel;
+        const bool nb = on && (e < best);
+        best = nb ? e : best;
+        kb = nb ? s : kb;
+      }
+      // state at the best, kept lazily: written out (to the trajectory's row of best_states) only
+      // when the walk has left the best state by the end of the block
+      bool at_best = sh.atbest[rr] != 0u;
+      bool copy = false;
+      uint32_t wb = xw0;
+      if (kb >= 0) {
+        const uint32_t le = (2u << kb) - 1u;  // flips up to and including the best one
+        at_best = (acc & ~le) == 0u;
+        copy = !at_best;
+        wb = xw0 ^ (acc & le);
+      } else if (at_best && acc != 0u) {
+        copy = true;  // the first flip of the block left the best state
+        at_best = false;
+      }
+      // the copies are made by the whole warp, one trajectory after the other (lane = word)
+      uint32_t cm = __ballot_sync(0xffffffffu, copy && tv && lead);
+      while (cm) {
+        const int cl = __ffs(cm) - 1;
+        cm &= cm - 1u;
+        const int cr = dwarp + DW * (cl / NSEG);
+        const uint32_t wbr = __shfl_sync(0xffffffffu, wb, cl);
+        uint32_t *const xb = p.best_states + (batch0 + (uint64_t)cr) * (uint64_t)p.nw;
+        for (int k = lane; k < nblk; k += 32)
+          xb[k] = (k == b) ? wbr : sh.x[k][cr];  // sh.x[b] still holds the spins before this block
+      }
+      __syncwarp();
+      if (lead) {
+        sh.erel[r] = erel;
+        sh.best[r] = best;
+        sh.atbest[r] = at_best ? 1u : 0u;
+        sh.x[b][r] = xw0 ^ acc;
+        s_acc[par][r] = acc;
+        s_sign[par][r] = acc & xw0;  // spins that were 1 before their flip: sign -1
+        const uint32_t na = sh.naccept[r] + (uint32_t)__popc(acc);
+        sh.naccept[r] = na;
+        if (na >= 0x80000000u) {
+          atomicAdd(&p.counters->accepts, (unsigned long long)na);
+          sh.naccept[r] = 0u;
+        }
+      }
+      pa = acc;
+      ps = acc & xw0;
+      return t0;
+    };
+
+    // Barriers: #0 initial spins and scales are in shared memory; B(-1) snapshots of blocks 0
+    // and 1, thresholds and tiles of block 0 are ready; B(j) masks of block j are ready (j = 0:
+    // the apply warps have been waiting), thresholds and tiles of block j+1 are ready.
+    bar_cta();  // #0
+    BlockIt nxt{0, 0, 0, PT ? p.step_base : 0u};
+    prepare(nxt, 0);
+    bar_cta();  // B(-1)
+    {
+      int b = 0;
+      for (long long j = 0; j < total_blocks; ++j) {
+        const long long t0 = walk(j, b);
+        b = (b + 1 == nblk) ? 0 : b + 1;
+        advance(nxt);
+        if (j + 1 < total_blocks) prepare(nxt, (int)((j + 1) & 1));
+        t_decide += clock64() - t0;
+        bar_cta();  // B(j)
       }
     }
     // ---- results ----
-#pragma unroll 1
-    for (int rr = 0; rr < TPD; ++rr) {
-      const int r = dwarp + rr * WS_DECIDE_WARPS;
-      if (r < R && r < nvalid) {
-        if (s_atbest[r]) {
-          for (int k = lane; k < nblk; k += 32) s_xb[r][k] = s_x[r][k];
-        }
-        __syncwarp();
-        const uint64_t tl = batch0 + (uint64_t)r;
-        for (int k = lane; k < p.nw; k += 32) p.best_states[tl * (uint64_t)p.nw + k] = s_xb[r][k];
-        if (PT && p.final_states)
-          for (int k = lane; k < p.nw; k += 32) p.final_states[tl * (uint64_t)p.nw + k] = s_x[r][k];
-        if (lane == 0) p.best_rel[tl] = s_best[r];
-      }
+    for (int q = 0; q < nvalid; ++q) {
+      const uint64_t row = batch0 + (uint64_t)q;
+      if (sh.atbest[q])
+        for (int k = dt; k < p.nw; k += DT) p.best_states[row * (uint64_t)p.nw + k] = sh.x[k][q];
+      if (PT && p.final_states)
+        for (int k = dt; k < p.nw; k += DT) p.final_states[row * (uint64_t)p.nw + k] = sh.x[k][q];
+      if (dt == 0) p.best_rel[row] = sh.best[q];
     }
-    if (lane == 0) {
-      if (cnt_acc) atomicAdd(&p.counters->accepts, cnt_acc);
-      if (dwarp == 0) atomicAdd(&p.counters->cyc_decide, (unsigned long long)t_decide);
-      if (dwarp == 0 && (p.debug_flags & 8)) atomicAdd(&p.counters->pad, n_walk);
+    if (dt < R && sh.naccept[dt])
+      atomicAdd(&p.counters->accepts, (unsigned long long)sh.naccept[dt]);
+    if (dt == 0) {
+      atomicAdd(&p.counters->cyc_decide, (unsigned long long)t_decide);
+      if (p.debug_flags & 8) {  // walk phases of decide warp 0 instead of the apply-role timers
+        atomicAdd(&p.counters->cyc_init, (unsigned long long)t_catch);
+        atomicAdd(&p.counters->cyc_stage, (unsigned long long)t_sites);
+      }
     }
   }
 }
@@ -452,7 +532,8 @@ cudaError_t launch_ws(const DenseParams<T> &p, cudaStream_t s, LaunchInfo *info)
   constexpr int WS_THREADS = WsRegs<DW>::THREADS;
   const uint64_t grid64 = (p.num_tries + R - 1) / R;
   if (grid64 == 0 || grid64 > 0x7fffffffull) return cudaErrorInvalidValue;
-  const size_t smem = (size_t)K * NCH * WS_APPLY_THREADS * 16;
+  const size_t smem = (size_t)WsRing<T, NCH, R, K>::KE * NCH * WS_APPLY_THREADS * 16 +
+                      sizeof(WsTiles<T>);
   // the resumable instantiation only when a per-trajectory scale is given (osa_pt_anneal)
   auto kern = p.tscale_traj ? k_dense_seq_ws<T, NCH, R, K, G, true, DW>
                             : k_dense_seq_ws<T, NCH, R, K, G, false, DW>;
