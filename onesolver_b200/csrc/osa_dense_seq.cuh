@@ -82,6 +82,23 @@ struct CopyPieces<NCH, SSTEP, GSTEP, NCH> {
   static __device__ __forceinline__ void issue(uint32_t, const void *) {}
 };
 
+// NCH reads of 16 bytes from the shared-memory address + c*SSTEP (offsets as immediates)
+__device__ __forceinline__ void lds16(uint32_t addr, int off, float *o) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3])
+               : "r"(addr + off));
+}
+__device__ __forceinline__ void lds16(uint32_t addr, int off, double *o) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(o[0]), "=d"(o[1]) : "r"(addr + off));
+}
+template <typename T, int NCH, int SSTEP>
+struct LoadPieces {
+  static __device__ __forceinline__ void load(uint32_t addr, T *out) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) lds16(addr, c * SSTEP, out + c * Vec16<T>::V);
+  }
+};
+
 // P2: stream the rows of block i0 whose site was accepted by at least one trajectory
 // and apply them.  am[r] bit s: trajectory r flipped site i0+s; sm[r] bit s: the spin
 // was 1 before the flip (sign -1).
@@ -129,16 +146,16 @@ __device__ __forceinline__ uint32_t apply_rows(const T *__restrict__ qoff, unsig
   }
 
   // addresses: one 64-bit base per block, a 32-bit row offset per row, immediates per piece;
-  // the ring is walked with wrapping byte addresses (no per-row multiplications)
+  // the ring is walked with wrapping 32-bit shared-memory addresses (no per-row multiplications).
+  // The two bases go through an empty asm so that the compiler keeps them in registers: left to
+  // itself it recomputes both from the kernel parameters and the thread id for every row.
   const unsigned char *base =
       reinterpret_cast<const unsigned char *>(qoff + (size_t)i0 * ld + (size_t)tid * V);
+  uint32_t ring_lo = smem_addr(ring + (size_t)tid * 16);
+  asm volatile("" : "+l"(base), "+r"(ring_lo));
   const uint32_t row_bytes = (uint32_t)(ld * sizeof(T));
-  const unsigned char *r_lo = ring + (size_t)tid * 16;
-  const unsigned char *r_hi = r_lo + (size_t)K * ROW_BYTES;
-  const unsigned char *r_ptr = r_lo;
-  const uint32_t w_lo = smem_addr(r_lo);
-  const uint32_t w_hi = w_lo + (uint32_t)K * ROW_BYTES;
-  uint32_t w_addr = w_lo;
+  const uint32_t ring_hi = ring_lo + (uint32_t)K * ROW_BYTES;
+  uint32_t r_addr = ring_lo, w_addr = ring_lo;
   uint32_t rem_issue = any, rem_apply = any;
 
   auto issue_next = [&]() {
@@ -148,7 +165,7 @@ __device__ __forceinline__ uint32_t apply_rows(const T *__restrict__ qoff, unsig
       const unsigned char *rp = base + (uint32_t)s * row_bytes;
       CopyPieces<NCH, TH * 16, CHW * (int)sizeof(T)>::issue(w_addr, rp);
       w_addr += ROW_BYTES;
-      if (w_addr == w_hi) w_addr = w_lo;
+      if (w_addr == ring_hi) w_addr = ring_lo;
     }
     asm volatile("cp.async.commit_group;" ::: "memory");  // one group per step, empty or not
   };
@@ -162,11 +179,9 @@ __device__ __forceinline__ uint32_t apply_rows(const T *__restrict__ qoff, unsig
     // arithmetic of the next copies
     asm volatile("cp.async.wait_group %0;" ::"n"(K - 2) : "memory");
     T qv[NCH * V];
-#pragma unroll
-    for (int c = 0; c < NCH; ++c)
-      vec_unpack<T>(*reinterpret_cast<const VecT *>(r_ptr + c * (TH * 16)), &qv[c * V]);
-    r_ptr += ROW_BYTES;
-    if (r_ptr == r_hi) r_ptr = r_lo;
+    LoadPieces<T, NCH, TH * 16>::load(r_addr, qv);
+    r_addr += ROW_BYTES;
+    if (r_addr == ring_hi) r_addr = ring_lo;
     issue_next();
     const int s = __ffs(rem_apply) - 1;
     rem_apply &= rem_apply - 1;

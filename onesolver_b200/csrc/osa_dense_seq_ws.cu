@@ -60,6 +60,52 @@ __device__ __forceinline__ void bar_named(int id) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(THREADS) : "memory");
 }
 
+// Sign / mask arithmetic on the bit patterns of the fields.  The walk of the decide warps keeps
+// its dependency chain free of predicates (a predicate costs ~13 cycles from its compare to the
+// instruction it guards): "dE < theta" is the sign bit of the rounded difference dE - theta
+// (exact in sign: without flush-to-zero a difference of two different numbers never rounds to
+// zero, and theta > 0), turned into an all-ones / all-zeros mask; an accepted flip multiplies the
+// tile row by +-1.0, a rejected one by +0.0 (h + 0*q == h).
+template <typename T>
+struct Bits;
+template <>
+struct Bits<float> {
+  static __device__ __forceinline__ float neg_if(float x, uint32_t bit) {  // bit ? -x : x
+    return __uint_as_float(__float_as_uint(x) ^ (bit << 31));
+  }
+  static __device__ __forceinline__ uint32_t neg_mask(float d) {  // sign bit set ? ~0 : 0
+    return (uint32_t)((int)__float_as_uint(d) >> 31);
+  }
+  static __device__ __forceinline__ float unit(uint32_t bit, uint32_t mask) {  // mask ? (bit ? -1 : 1) : 0
+    return __uint_as_float((0x3f800000u | (bit << 31)) & mask);
+  }
+  static __device__ __forceinline__ float masked(float x, uint32_t mask) {
+    return __uint_as_float(__float_as_uint(x) & mask);
+  }
+  static __device__ __forceinline__ float bcast(float m, int src, uint32_t mask) {
+    return __uint_as_float(__shfl_sync(0xffffffffu, __float_as_uint(m), src) & mask);
+  }
+};
+template <>
+struct Bits<double> {
+  static __device__ __forceinline__ double neg_if(double x, uint32_t bit) {
+    return __hiloint2double(__double2hiint(x) ^ (int)(bit << 31), __double2loint(x));
+  }
+  static __device__ __forceinline__ uint32_t neg_mask(double d) {
+    return (uint32_t)(__double2hiint(d) >> 31);
+  }
+  static __device__ __forceinline__ double unit(uint32_t bit, uint32_t mask) {
+    return __hiloint2double((int)((0x3ff00000u | (bit << 31)) & mask), 0);
+  }
+  static __device__ __forceinline__ double masked(double x, uint32_t mask) {
+    return __hiloint2double((int)((uint32_t)__double2hiint(x) & mask),
+                            (int)((uint32_t)__double2loint(x) & mask));
+  }
+  static __device__ __forceinline__ double bcast(double m, int src, uint32_t mask) {  // m is +-1 or 0
+    return __hiloint2double((int)(__shfl_sync(0xffffffffu, (uint32_t)__double2hiint(m), src) & mask), 0);
+  }
+};
+
 // HS consecutive elements from a (HS * sizeof(T))-byte aligned shared-memory address
 template <typename T, int HS>
 __device__ __forceinline__ void load_seg(const T *src, T (&out)[HS]) {
@@ -301,8 +347,9 @@ __global__ void __launch_bounds__(WsRegs<DW>::THREADS, 1) k_dense_seq_ws(const D
     };
 
     // thresholds and tiles of block c into the buffers of parity `buf` (all decide threads).  The
-    // tiles go straight from L2 to shared memory (cp.async) while the thresholds are computed.
-    auto prepare = [&](const BlockIt &c, int buf) {
+    // tiles go straight from L2 to shared memory (cp.async, issued before the walk of the current
+    // block); the thresholds are computed after the walk.
+    auto prepare_tiles = [&](const BlockIt &c, int buf) {
       const int i0 = c.b * 32;
       const int bp = (c.b == 0) ? nblk - 1 : c.b - 1;  // previous block (cyclic)
       for (int qi = dt; qi < TILE_VECS; qi += DT) {
@@ -314,6 +361,9 @@ __global__ void __launch_bounds__(WsRegs<DW>::THREADS, 1) k_dense_seq_ws(const D
                      "l"(p.qoff + (size_t)(bp * 32 + row) * p.ld + i0 + cv * V)
                      : "memory");
       }
+    };
+    auto prepare_thresholds = [&](const BlockIt &c, int buf) {
+      const int i0 = c.b * 32;
       // one Philox block serves four consecutive sites of a trajectory (STREAM_SEQ: c0 = site>>2)
       const T ts = PT ? (T)0 : p.tscale[c.iter];
       for (int q = dt; q < R * 8; q += DT) {
@@ -362,20 +412,18 @@ __global__ void __launch_bounds__(WsRegs<DW>::THREADS, 1) k_dense_seq_ws(const D
       for (int k = 0; k < HS; ++k) hs[k] = sh.snap[par][c0 + k][rr];
       // bring the snapshot up to date: the rows of block j-1 that the trajectory flipped, in site
       // order -- the same fma sequence the apply warps run on these columns, hence the same bits.
-      // Branch-free over the 32 sites, so that the loads run ahead of the arithmetic.
+      // Branch-free over the 32 sites, so that the loads run ahead of the arithmetic: a lane
+      // whose trajectory did not flip the site multiplies the row by zero.  (Visiting only the
+      // flipped sites, a warp-uniform ffs loop, was measured slower: profiles/r01/probe_v30*.)
       {
         const T(*tx)[WsTiles<T>::TP] = tl.tile_x[par];
 #pragma unroll
         for (int s = 0; s < 32; ++s) {
-          const bool on = ((pa >> s) & 1u) != 0u;
-          const T sgn = ((ps >> s) & 1u) ? (T)-1 : (T)1;
+          const T m = Bits<T>::unit((ps >> s) & 1u, 0u - ((pa >> s) & 1u));  // +-1 if flipped, else 0
           T qv[HS];
           load_seg<T, HS>(&tx[s][c0], qv);
 #pragma unroll
-          for (int k = 0; k < HS; ++k) {
-            const T up = det::fma(sgn, qv[k], hs[k]);
-            hs[k] = on ? up : hs[k];
-          }
+          for (int k = 0; k < HS; ++k) hs[k] = det::fma(m, qv[k], hs[k]);
         }
       }
       if (p.debug_flags & 8) {
@@ -383,47 +431,38 @@ __global__ void __launch_bounds__(WsRegs<DW>::THREADS, 1) k_dense_seq_ws(const D
         t_catch += now - tp;
         tp = now;
       }
-      // the walk: phase ph decides the sites of segment ph, site by site; an accepted flip adds
-      // the row of the diagonal tile to the fields of the later sites -- in the deciding lane for
-      // its own segment, in the lanes of the later segments after a ballot
+      // the walk: phase ph decides the sites of segment ph, site by site.  An accepted flip adds
+      // the row of the diagonal tile to the fields of the later sites: at once in the deciding
+      // lane (its own segment), at the end of the phase in the lanes of the later segments, which
+      // receive the multipliers of the phase by shuffles that were issued along the way.
       uint32_t acc = 0u;
       const T(*td)[WsTiles<T>::TP] = tl.tile_d[par];
 #pragma unroll
       for (int ph = 0; ph < NSEG; ++ph) {
+        const uint32_t mine = (tv && seg == ph) ? 0xffffffffu : 0u;
+        const uint32_t later = (seg > ph) ? 0xffffffffu : 0u;
+        T qv[HS][HS], mo[HS];
 #pragma unroll
         for (int s = 0; s < HS; ++s) {
           const int site = ph * HS + s;
-          if (ph + 1 == NSEG && s + 1 == HS) {  // last site: nothing left to update
-            const T th = sh.theta[par][site][rr];
-            const bool xl = ((xw0 >> site) & 1u) != 0u;
-            const T dE = xl ? -hs[s] : hs[s];
-            const bool okm = tv && (seg == ph) && (i0 + site < n) && (dE < th);
-            if (okm) sh.dE[site][rr] = dE;
-            acc |= okm ? (1u << site) : 0u;
-            continue;
-          }
           const T th = sh.theta[par][site][rr];
-          const bool xl = ((xw0 >> site) & 1u) != 0u;  // a site flips at most once per block
-          const T dE = xl ? -hs[s] : hs[s];
-          const bool okm = tv && (seg == ph) && (i0 + site < n) && (dE < th);
-          if (okm) sh.dE[site][rr] = dE;
-          bool okp = false;  // the decision of my trajectory, seen from a later segment
-          if (ph + 1 < NSEG) {
-            const uint32_t bal = __ballot_sync(0xffffffffu, okm);
-            okp = (seg > ph) && (((bal >> (t * NSEG + ph)) & 1u) != 0u);
-          }
-          const T sgn = xl ? (T)-1 : (T)1;
-          T qv[HS];
-          load_seg<T, HS>(&td[site][c0], qv);
+          const uint32_t xl = (xw0 >> site) & 1u;  // a site flips at most once per block
+          const T dE = Bits<T>::neg_if(hs[s], xl);
+          const uint32_t ok = Bits<T>::neg_mask(det::add(dE, -th)) & mine &
+                              ((i0 + site < n) ? 0xffffffffu : 0u);
+          const T m = Bits<T>::unit(xl, ok);
+          if (has && seg == ph) sh.dE[site][rr] = Bits<T>::masked(dE, ok);  // 0 when rejected
+          acc |= ok & (1u << site);
+          if (ph + 1 < NSEG || s + 1 < HS) load_seg<T, HS>(&td[site][c0], qv[s]);
 #pragma unroll
-          for (int k = 0; k < HS; ++k) {
-            if (k > s || ph + 1 < NSEG) {
-              const bool pr = (k > s) ? (okm || okp) : okp;
-              const T up = det::fma(sgn, qv[k], hs[k]);
-              hs[k] = pr ? up : hs[k];
-            }
-          }
-          acc |= okm ? (1u << site) : 0u;
+          for (int k = s + 1; k < HS; ++k) hs[k] = det::fma(m, qv[s][k], hs[k]);
+          if (ph + 1 < NSEG) mo[s] = Bits<T>::bcast(m, t * NSEG + ph, later);
+        }
+        if (ph + 1 < NSEG) {
+#pragma unroll
+          for (int s = 0; s < HS; ++s)
+#pragma unroll
+            for (int k = 0; k < HS; ++k) hs[k] = det::fma(mo[s], qv[s][k], hs[k]);
         }
       }
       // every lane of a trajectory gets the whole accept mask
@@ -434,12 +473,12 @@ __global__ void __launch_bounds__(WsRegs<DW>::THREADS, 1) k_dense_seq_ws(const D
       // erel += dE in site order, kb = site of the last flip that set a new best (strict <)
       double erel = sh.erel[rr], best = sh.best[rr];
       int kb = -1;
+      __syncwarp();  // sh.dE of the block is complete
 #pragma unroll
       for (int s = 0; s < 32; ++s) {
-        const bool on = ((acc >> s) & 1u) != 0u;
-        const double e = det::add(erel, (double)sh.dE[s][rr]);
-        erel = on ? e : erel;
-        const bool nb = on && (e < best);
+        const double e = det::add(erel, (double)sh.dE[s][rr]);  // dE is +0 for a rejected site
+        erel = e;
+        const bool nb = e < best;  // never true without a flip: best <= erel
         best = nb ? e : best;
         kb = nb ? s : kb;
       }
@@ -493,15 +532,18 @@ __global__ void __launch_bounds__(WsRegs<DW>::THREADS, 1) k_dense_seq_ws(const D
     // the apply warps have been waiting), thresholds and tiles of block j+1 are ready.
     bar_cta();  // #0
     BlockIt nxt{0, 0, 0, PT ? p.step_base : 0u};
-    prepare(nxt, 0);
+    prepare_tiles(nxt, 0);
+    prepare_thresholds(nxt, 0);
     bar_cta();  // B(-1)
     {
       int b = 0;
       for (long long j = 0; j < total_blocks; ++j) {
+        advance(nxt);
+        const bool more = j + 1 < total_blocks;
+        if (more) prepare_tiles(nxt, (int)((j + 1) & 1));
         const long long t0 = walk(j, b);
         b = (b + 1 == nblk) ? 0 : b + 1;
-        advance(nxt);
-        if (j + 1 < total_blocks) prepare(nxt, (int)((j + 1) & 1));
+        if (more) prepare_thresholds(nxt, (int)((j + 1) & 1));
         t_decide += clock64() - t0;
         bar_cta();  // B(j)
       }
