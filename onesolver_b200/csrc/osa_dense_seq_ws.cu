@@ -594,14 +594,13 @@ cudaError_t launch_ws(const DenseParams<T> &p, cudaStream_t s, LaunchInfo *info)
   return cudaGetLastError();
 }
 
-// decide warps for the shapes with <= 3 column groups per thread (N <= 3072 fp32 / 1536 fp64),
-// where the decisions, not the row streaming, bound the kernel; OSA_WS_DW=4 for A/B runs
+// decide warps for the shapes with <= 3 column groups per thread (N <= 3072 fp32 / 1536 fp64):
+// 4 like everywhere else.  With the walk-per-lane decide role the SM is issue-bound at these
+// sizes and 8 decide warps only add instructions (N = 1024 fp64: 2.40 -> 2.30 ms for the probe,
+// profiles/r01/probe_v31*.log); OSA_WS_DW=8 keeps the old choice for A/B runs.
 int decide_warps_small_n() {
-  static const int dw = [] {
-    const char *e = getenv("OSA_WS_DW");
-    return (e && atoi(e) == 4) ? 4 : 8;
-  }();
-  return dw;
+  const char *e = getenv("OSA_WS_DW");
+  return (e && atoi(e) == 8) ? 8 : 4;
 }
 
 }  // namespace
