@@ -185,6 +185,41 @@ __global__ void __launch_bounds__(256) k_cpasync(const uint4 *q, int rows, int r
   if (acc == 0x12345678u) *sink = acc;
 }
 
+// The same ring, but every CTA walks the rows in its own order (row = (a*j + b) mod rows with a
+// per-CTA odd multiplier; rows must be a power of two): the CTAs of the sweep kernel do not ask for
+// the same row at the same time, which is what the "same sequence" probes above measure.
+template <int K>
+__global__ void __launch_bounds__(256) k_cpasync_perm(const uint4 *q, int rows, int row_vec, int iters, unsigned *sink) {
+  extern __shared__ __align__(128) unsigned char ring[];
+  const int t = threadIdx.x;
+  unsigned acc = 0;
+  uint4 *mine = reinterpret_cast<uint4 *>(ring);
+  const unsigned a = (blockIdx.x * 2654435761u) | 1u, b = blockIdx.x * 40503u + 17u, mask = rows - 1;
+  auto issue = [&](int j, int slot) {
+    const unsigned r = (a * (unsigned)j + b) & mask;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const uint32_t dst = smem_u32(mine + (size_t)slot * 1024 + v * 256 + t);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(q + (size_t)r * row_vec + v * 256 + t) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  for (int it = 0; it < iters; ++it) {
+    for (int k = 0; k < K - 1; ++k) issue(k, k);
+    for (int j = 0; j < rows; ++j) {
+      if (j + K - 1 < rows) issue(j + K - 1, (j + K - 1) % K);
+      else asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group %0;" ::"n"(K - 1) : "memory");
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const uint4 x = mine[(size_t)(j % K) * 1024 + v * 256 + t];
+        acc ^= x.x + x.y + x.z + x.w;
+      }
+    }
+  }
+  if (acc == 0x12345678u) *sink = acc;
+}
+
 // ---- TMA ring ----
 __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -433,6 +468,10 @@ int main(int argc, char **argv) {
       runc(k_cpasync<6>, 6, "cpasync_k6");
       runc(k_cpasync<8>, 8, "cpasync_k8");
       runc(k_cpasync<12>, 12, "cpasync_k12");
+      if ((rows & (rows - 1)) == 0) {
+        runc(k_cpasync_perm<6>, 6, "cpasync_k6_own_order");
+        runc(k_cpasync_perm<12>, 12, "cpasync_k12_own_order");
+      }
     }
     report("ldg_depth4_2cta_per_sm", 2 * sms, time_ms([&] { k_ldg<4, 4><<<2 * sms, 256>>>((uint4 *)q, rows, row_vec, iters, 0, sink); }));
   }
