@@ -1,0 +1,49 @@
+"""CPU tests of bench.py's host logic: argument contract and the workload specifications of the
+three GPU configurations of BASELINE.json (no compute calls)."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def _args(**kw):
+    base = dict(gpus=1, steps=1, warmup=0, impl="engine", workload="config5", n=4096,
+                tries_per_gpu=131072, sweeps=32, beta_min=1.28, beta_max=19.2, precision="f32",
+                no_cpu_baseline=True, no_e2e=True)
+    base.update(kw)
+    return argparse.Namespace(**base)
+
+
+def test_default_workload_is_baseline_config5_share():
+    cfg = bench.config_dict(_args(), 8)
+    assert cfg["n"] == 4096 and cfg["tries_per_gpu"] == 131072 and 8 * cfg["tries_per_gpu"] == 1 << 20
+    assert "config 5" in cfg["workload"] and cfg["parallelism"].startswith("trajectory shards x8")
+    sched = bench.make_schedule(_args())
+    assert len(sched) == 32 and np.isclose(sched[0], 1.28)
+
+
+def test_config3_and_config4_specs_match_baseline_shapes():
+    s3 = bench.other_config_spec(_args(workload="config3"))
+    assert (s3["n"], s3["tries"], s3["sweeps"], s3["dtype"]) == (1024, 16384, 1000, "f64")
+    assert s3["host_input"].shape == (1024, 1024) and len(s3["sched"]) == 1000
+    assert np.allclose(s3["host_input"], s3["host_input"].T)
+    s4 = bench.other_config_spec(_args(workload="config4"))
+    assert (s4["n"], s4["tries"], s4["sweeps"]) == (5627, 65536, 100)
+    assert s4["nnz"] % 2 == 0 and 35000 <= s4["nnz"] // 2 <= 45000  # ~40k couplers, SURVEY 8(d)
+    d = np.diff(s4["sched"])
+    assert np.allclose(d, d[0])  # linear schedule
+
+
+def test_reference_arm_of_other_configs_reports_unavailable():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                        "--workload", "config4"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and "unavailable" in line
