@@ -183,9 +183,8 @@ __device__ __forceinline__ uint32_t apply_rows(const T *__restrict__ qoff, unsig
     r_addr += ROW_BYTES;
     if (r_addr == ring_hi) r_addr = ring_lo;
     issue_next();
-    const int s = __ffs(rem_apply) - 1;
-    rem_apply &= rem_apply - 1;
-    const uint32_t bit = 1u << s;
+    const uint32_t bit = rem_apply & (0u - rem_apply);  // lowest site not yet applied
+    rem_apply ^= bit;
     if (DBG == 1) {  // timing experiment: touch the data, skip the arithmetic
       T acc = (T)0;
 #pragma unroll
