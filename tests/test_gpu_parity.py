@@ -112,6 +112,46 @@ def test_dense_seq_bit_exact(gpu, n, dtype, tries, sweeps):
     assert cnt.accepts > 0
 
 
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 63, 64, 65])
+@pytest.mark.parametrize("mode", [capi.MODE_RANDOM_SITE, capi.MODE_SEQUENTIAL_SWEEP])
+def test_tiny_and_block_boundary_sizes(gpu, n, mode):
+    """N around the 32-site block / spin-word boundary (and N = 1), a number of tries that is not a
+    multiple of the trajectories per CTA, and a single trajectory; integer coefficients, so fp32
+    and fp64 fields give the reference energies exactly."""
+    rng = np.random.default_rng(n)
+    a = rng.integers(-5, 6, size=(n, n)).astype(np.float64)
+    q = np.triu(a, 1)
+    q = q + q.T + np.diag(np.diag(a))
+    sched = ob.ref_schedule("linear", 0.5, 5.0, 6)
+    for dtype in (np.float64, np.float32):
+        for tries in (37, 1):
+            res, _ = run_and_compare_dense(q, sched, 6, tries, mode, dtype)
+            assert (res.best_energies == ob.energy_packed(q, res.best_states_packed)).all()
+
+
+def test_sparse_tiny_sizes_and_isolated_sites(gpu):
+    """CSR instances with fewer sites than a block, a site without neighbours and one trajectory."""
+    cases = [gen.sparse_random_graph(n, deg, seed=900 + n, integer=True) + (tries,)
+             for n, deg, tries in [(2, 1, 5), (7, 2, 33), (33, 3, 1), (65, 4, 40)]]
+    # five sites on a path 0-1, 3-4 with site 2 isolated (empty CSR row), and a single site
+    cases.append((np.array([0, 1, 2, 2, 3, 4], dtype=np.int64), np.array([1, 0, 4, 3], dtype=np.int32),
+                  np.array([2.0, 2.0, -3.0, -3.0]), np.array([-1.0, 1.0, -2.0, 1.0, 1.0]), 9))
+    cases.append((np.array([0, 0], dtype=np.int64), np.array([], dtype=np.int32), np.array([]),
+                  np.array([-4.0]), 3))
+    for rowptr, col, val, diag, tries in cases:
+        n = len(diag)
+        sched = ob.ref_schedule("linear", 0.5, 5.0, 5)
+        for mode in (capi.MODE_SEQUENTIAL_SWEEP, capi.MODE_RANDOM_SITE):
+            with Problem.csr(rowptr, col, val, diag, sweep_precision=capi.SWEEP_F64) as prob:
+                res = prob.anneal(sched, 5, tries, mode=mode, want_energies=True, want_states=True)
+            _, best, _, cnt = ob.replay_csr(rowptr, col, val, diag, sched, 5, tries, mode=mode,
+                                            dtype=np.float64)
+            assert_states_equal(res.best_states_packed, best, f"sparse n={n}")
+            assert res.stats["accepts"] == cnt.accepts
+            q = gen.csr_to_dense(rowptr, col, val, diag)
+            assert (res.best_energies == ob.energy_packed(q, best)).all()
+
+
 def test_dense_seq_sweeps_per_beta_and_boltzmann(gpu):
     q = gen.dense_uniform_qubo(200, seed=5)
     sched = ob.ref_schedule("linear", 0.05, 2.0, 4)
