@@ -2,6 +2,8 @@
 // (osa_dense_seq.cu: single-role CTA; osa_dense_seq_ws.cu: warp-specialised decide/apply overlap).
 #pragma once
 
+#include <type_traits>
+
 #include "osa_common.cuh"
 
 namespace osa {
@@ -172,8 +174,8 @@ __device__ __forceinline__ uint32_t apply_rows(const T *__restrict__ qoff, unsig
 
 #pragma unroll 1
   for (int k = 0; k < K - 1; ++k) issue_next();
-#pragma unroll 1
-  while (rem_apply) {
+  // one step: wait for the oldest row, read it, (request one more row,) apply it
+  auto step = [&](auto more) {
     // row i has landed when at most K-2 younger groups are pending; read it into registers
     // first, so that the latency of the shared-memory loads hides behind the address
     // arithmetic of the next copies
@@ -182,7 +184,15 @@ __device__ __forceinline__ uint32_t apply_rows(const T *__restrict__ qoff, unsig
     LoadPieces<T, NCH, TH * 16>::load(r_addr, qv);
     r_addr += ROW_BYTES;
     if (r_addr == ring_hi) r_addr = ring_lo;
-    issue_next();
+    if constexpr (decltype(more)::value) {
+      const int s = __ffs(rem_issue) - 1;
+      rem_issue &= rem_issue - 1;
+      const unsigned char *rp = base + (uint32_t)s * row_bytes;
+      CopyPieces<NCH, TH * 16, CHW * (int)sizeof(T)>::issue(w_addr, rp);
+      w_addr += ROW_BYTES;
+      if (w_addr == ring_hi) w_addr = ring_lo;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");  // one group per step, empty or not
     const uint32_t bit = rem_apply & (0u - rem_apply);  // lowest site not yet applied
     rem_apply ^= bit;
     if (DBG == 1) {  // timing experiment: touch the data, skip the arithmetic
@@ -190,7 +200,7 @@ __device__ __forceinline__ uint32_t apply_rows(const T *__restrict__ qoff, unsig
 #pragma unroll
       for (int e = 0; e < NCH * V; ++e) acc += qv[e];
       if (acc == (T)123456789) h[0].set(0, acc);
-      continue;
+      return;
     }
 #pragma unroll
     for (int g = 0; g < R / G; ++g) {
@@ -203,7 +213,12 @@ __device__ __forceinline__ uint32_t apply_rows(const T *__restrict__ qoff, unsig
         }
       }
     }
-  }
+  };
+  // while rows are left to request every step requests one; the last K-1 rows only drain
+#pragma unroll 1
+  while (rem_issue) step(std::true_type{});
+#pragma unroll 1
+  while (rem_apply) step(std::false_type{});
   return any;
 }
 
