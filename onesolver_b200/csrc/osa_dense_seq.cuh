@@ -160,7 +160,9 @@ __device__ __forceinline__ uint32_t apply_rows(const T *__restrict__ qoff, unsig
   uint32_t r_addr = ring_lo, w_addr = ring_lo;
   uint32_t rem_issue = any, rem_apply = any;
 
-  auto issue_next = [&]() {
+  // ring fill: the first K-1 requests of the block (fewer when the block has fewer rows)
+#pragma unroll 1
+  for (int k = 0; k < K - 1; ++k) {
     if (rem_issue) {
       const int s = __ffs(rem_issue) - 1;
       rem_issue &= rem_issue - 1;
@@ -170,10 +172,20 @@ __device__ __forceinline__ uint32_t apply_rows(const T *__restrict__ qoff, unsig
       if (w_addr == ring_hi) w_addr = ring_lo;
     }
     asm volatile("cp.async.commit_group;" ::: "memory");  // one group per step, empty or not
+  }
+
+  // In the loop the address of a request is prepared one step ahead (rp_next), so that the
+  // ffs -> multiply -> add chain is off the path of the copies.  (Doing the same in the fill
+  // was measured slower: profiles/r01/probe_v51*.log.)
+  const unsigned char *rp_next = base + (uint32_t)(__ffs(rem_issue) - 1) * row_bytes;
+  auto request = [&]() {  // requires rem_issue != 0
+    CopyPieces<NCH, TH * 16, CHW * (int)sizeof(T)>::issue(w_addr, rp_next);
+    w_addr += ROW_BYTES;
+    if (w_addr == ring_hi) w_addr = ring_lo;
+    rem_issue &= rem_issue - 1;
+    rp_next = base + (uint32_t)(__ffs(rem_issue) - 1) * row_bytes;  // unused when none is left
   };
 
-#pragma unroll 1
-  for (int k = 0; k < K - 1; ++k) issue_next();
   // one step: wait for the oldest row, read it, (request one more row,) apply it
   auto step = [&](auto more) {
     // row i has landed when at most K-2 younger groups are pending; read it into registers
@@ -184,14 +196,7 @@ __device__ __forceinline__ uint32_t apply_rows(const T *__restrict__ qoff, unsig
     LoadPieces<T, NCH, TH * 16>::load(r_addr, qv);
     r_addr += ROW_BYTES;
     if (r_addr == ring_hi) r_addr = ring_lo;
-    if constexpr (decltype(more)::value) {
-      const int s = __ffs(rem_issue) - 1;
-      rem_issue &= rem_issue - 1;
-      const unsigned char *rp = base + (uint32_t)s * row_bytes;
-      CopyPieces<NCH, TH * 16, CHW * (int)sizeof(T)>::issue(w_addr, rp);
-      w_addr += ROW_BYTES;
-      if (w_addr == ring_hi) w_addr = ring_lo;
-    }
+    if constexpr (decltype(more)::value) request();
     asm volatile("cp.async.commit_group;" ::: "memory");  // one group per step, empty or not
     const uint32_t bit = rem_apply & (0u - rem_apply);  // lowest site not yet applied
     rem_apply ^= bit;
