@@ -333,13 +333,13 @@ def run_engine(args):
         q_bytes = args.n * ld * esz
         bound = "l2" if q_bytes <= 100 * (1 << 20) else "hbm"
         peak = l2_peak if bound == "l2" else peaks["hbm_gbs"]
-        # measured once with ncu at the default workload (profiles/r01/ncu_traffic_v46.csv)
+        # measured once with ncu at the default workload (profiles/r01/ncu_traffic_v54.csv)
         default_workload = (args.n == 4096 and tries == 131072 and args.sweeps == 32
                             and args.precision == "f32" and args.beta_min == 1.28
                             and args.beta_max == 19.2)
-        traffic = 132819331328 + 1674757632 if default_workload else None
+        traffic = 136361905408 + 1937762304 if default_workload else None
         traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum of one launch at this workload "
-                        "(ncu, profiles/r01/ncu_traffic_v46.csv): 0.13 TB of DRAM traffic against "
+                        "(ncu, profiles/r01/ncu_traffic_v54.csv): 0.14 TB of DRAM traffic against "
                         "14.08 TB of algorithmic row bytes, which are served by the L2 "
                         "(lts__t_sectors_srcunit_tex_op_read.sum x 32 B = 14.62 TB, hit rate 99.1%)"
                         if default_workload else "not captured for this workload")
