@@ -47,3 +47,39 @@ def test_reference_arm_of_other_configs_reports_unavailable():
     assert r.returncode == 0
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and "unavailable" in line
+
+
+# ---------------------------------------------------------------- committed bench lines
+ENGINE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step",
+               "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "roofline",
+               "clocks", "gpu_launches", "e2e"}
+
+
+def _last_json_line(path):
+    with open(path) as f:
+        return json.loads([ln for ln in f if ln.startswith("{")][-1])
+
+
+def test_committed_round_bench_lines_carry_the_contract_keys():
+    """The bench lines kept under profiles/ (what DESIGN.md quotes) have every key of the bench
+    contract: the headline line with roofline / e2e / cpu_baseline, the reference arm, and the
+    multi-GPU lines with a whole-job value."""
+    prof = os.path.join(ROOT, "profiles", "r01")
+    one = _last_json_line(os.path.join(prof, "bench_v52.json"))
+    assert ENGINE_KEYS <= set(one) and "cpu_baseline" in one
+    assert one["n_gpus"] == 1 and one["warmup"] >= 3 and one["config"]["workload"]
+    rf = one["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(rf)
+    assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(one["e2e"])
+    assert one["e2e"]["h2d_bytes_per_step"] >= 4096 * 4096 * 8  # the matrix is uploaded every step
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(one["cpu_baseline"])
+    assert not set(one["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    ref = _last_json_line(os.path.join(prof, "bench_ref_v52.json"))
+    assert ref["impl"] == "reference" and ref["metric"] == one["metric"] and ref["unit"] == one["unit"]
+    assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["kind"] in ("port", "reference")
+    for name, n in (("bench_v55_2gpu.json", 2), ("bench_v47_4gpu.json", 4), ("bench_v58_8gpu.json", 8)):
+        line = _last_json_line(os.path.join(prof, name))
+        assert ENGINE_KEYS <= set(line) and line["n_gpus"] == n and line["scaling"] == "weak"
+        # whole-job aggregate: close to n times the one-GPU value of the same round
+        assert 0.9 * n * 8.9e9 < line["value"] < 1.1 * n * one["value"]
