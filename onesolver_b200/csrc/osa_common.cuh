@@ -7,6 +7,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/onesolver_b200.h"
 
@@ -158,6 +159,8 @@ struct DenseParams {
   const T *tscale_traj;         // [num_tries]: per-trajectory threshold scale, replaces tscale[iter]
   uint32_t *final_states;       // [num_tries][nw]: spins after the last sweep (may alias init_states)
   uint32_t step_base;           // first sweep number of this launch in the STREAM_SEQ counter
+  // optional [num_tries]: FNV-1a hash of the trajectory's accepted flips (osa_anneal_traced)
+  unsigned long long *trace_hash;
   // timing experiments only (OSA_WS_DEBUG, tools/probe.py; results are meaningless when set):
   // 1 = the apply warps skip the row streaming (decide warps alone), 2 = the decide warps emit
   // pseudo-random accept masks of density 0.19 instead of deciding (apply warps alone),
@@ -189,6 +192,21 @@ struct SparseParams {
   Counters *counters;
 };
 
+// Timing-experiment switches that make the results of a call meaningless (skipped row streaming,
+// faked accept masks, loads-only instantiations) exist only in probe builds: -DOSA_PROBE, set by
+// tools/build_variant.sh for the libraries under build/ab/.  The in-tree library ignores them, so a
+// stray environment variable cannot corrupt results; only result-preserving tuning knobs
+// (OSA_DS_WS, OSA_WS_DW, OSA_WS_R, OSA_ENERGY_MMA) are read from the environment there.
+inline int probe_env_int(const char *name) {
+#ifdef OSA_PROBE
+  const char *e = getenv(name);
+  return e ? atoi(e) : 0;
+#else
+  (void)name;
+  return 0;
+#endif
+}
+
 // kernel ids reported in osa_stats.kernel_id
 enum KernelId : int {
   KID_AUTO = 0,
@@ -204,6 +222,8 @@ template <typename T>
 cudaError_t launch_dense_seq(const DenseParams<T> &p, cudaStream_t s, LaunchInfo *info);
 template <typename T>
 cudaError_t launch_dense_seq_ws(const DenseParams<T> &p, cudaStream_t s, LaunchInfo *info);
+template <typename T>
+cudaError_t launch_dense_seq_flow(const DenseParams<T> &p, cudaStream_t s, LaunchInfo *info);
 template <typename T>
 cudaError_t launch_dense_generic(const DenseParams<T> &p, cudaStream_t s, LaunchInfo *info);
 template <typename T>

@@ -306,11 +306,24 @@ static bool use_ws() {
   const char *e = getenv("OSA_DS_WS");
   return !(e && e[0] == '0');
 }
+// ... and of those, the free-running variant (osa_dense_seq_ws2.cu) unless OSA_WS_FLOW=0 asks for the
+// lock-step one (A/B runs; both give the same results bit for bit).
+#ifndef OSA_WS_FLOW_DEFAULT
+#define OSA_WS_FLOW_DEFAULT 0
+#endif
+static bool use_flow() {
+  const char *e = getenv("OSA_WS_FLOW");
+  return e ? e[0] != '0' : OSA_WS_FLOW_DEFAULT != 0;
+}
+template <typename T>
+static cudaError_t launch_ws_any(const DenseParams<T> &p, cudaStream_t s, LaunchInfo *info) {
+  return use_flow() ? launch_dense_seq_flow<T>(p, s, info) : launch_dense_seq_ws<T>(p, s, info);
+}
 
 template <>
 cudaError_t launch_dense_seq<float>(const DenseParams<float> &p, cudaStream_t s, LaunchInfo *info) {
   if (p.ld % 1024 != 0) return cudaErrorInvalidValue;
-  if (use_ws() && !getenv("OSA_DS_CFG")) return launch_dense_seq_ws<float>(p, s, info);
+  if (use_ws() && !getenv("OSA_DS_CFG")) return launch_ws_any<float>(p, s, info);
   switch (p.ld / 1024) {
     case 1: return launch_cfg<float, 1, 16, 16, 256, 4>(p, s, info);
     case 2: return launch_cfg<float, 2, 16, 16, 256, 4>(p, s, info);
@@ -323,7 +336,9 @@ cudaError_t launch_dense_seq<float>(const DenseParams<float> &p, cudaStream_t s,
         case 8122: return launch_cfg<float, 4, 8, 12, 256, 2>(p, s, info);
         case 8128: return launch_cfg<float, 4, 8, 12, 256, 8>(p, s, info);
         case 12122: return launch_cfg<float, 4, 12, 12, 256, 2>(p, s, info);
-        case 81211: return launch_cfg<float, 4, 8, 12, 256, 1, 1>(p, s, info);  // loads only (timing)
+#ifdef OSA_PROBE  // loads only (timing; results are meaningless): probe builds only
+        case 81211: return launch_cfg<float, 4, 8, 12, 256, 1, 1>(p, s, info);
+#endif
         default: return launch_cfg<float, 4, 8, 12, 256, 1>(p, s, info);
       }
     }
@@ -339,7 +354,7 @@ template <>
 cudaError_t launch_dense_seq<double>(const DenseParams<double> &p, cudaStream_t s,
                                      LaunchInfo *info) {
   if (p.ld % 512 != 0) return cudaErrorInvalidValue;
-  if (use_ws()) return launch_dense_seq_ws<double>(p, s, info);
+  if (use_ws()) return launch_ws_any<double>(p, s, info);
   switch (p.ld / 512) {
     case 1: return launch_cfg<double, 1, 16, 16, 256, 4>(p, s, info);
     case 2: return launch_cfg<double, 2, 16, 16, 256, 4>(p, s, info);

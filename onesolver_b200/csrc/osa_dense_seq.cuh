@@ -6,6 +6,10 @@
 
 #include "osa_common.cuh"
 
+#ifndef OSA_APPLY_VARIANT
+#define OSA_APPLY_VARIANT 0
+#endif
+
 namespace osa {
 namespace dseq {
 
@@ -24,6 +28,13 @@ struct Field<double, N> {
   __device__ __forceinline__ void axpy(double m, const double (&q)[N]) {
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = det::fma(m, q[i], v[i]);
+  }
+  // if (flag) v[i] += m * q[i], as predicated instructions (no branch)
+  __device__ __forceinline__ void axpy_if(uint32_t flag, double m, const double (&q)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p fma.rn.f64 %0, %1, %2, %0;\n\t}"
+          : "+d"(v[i]) : "d"(q[i]), "d"(m), "r"(flag));
   }
 };
 
@@ -47,6 +58,18 @@ struct Field<float, N> {
       const unsigned long long qq =
           ((unsigned long long)__float_as_uint(q[2 * i + 1]) << 32) | __float_as_uint(q[2 * i]);
       asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(p[i]) : "l"(qq), "l"(mm));
+    }
+  }
+  // if (flag) v[i] += m * q[i], as predicated instructions (no branch)
+  __device__ __forceinline__ void axpy_if(uint32_t flag, float m, const float (&q)[N]) {
+    const unsigned long long mb = __float_as_uint(m);
+    const unsigned long long mm = (mb << 32) | mb;
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+      const unsigned long long qq =
+          ((unsigned long long)__float_as_uint(q[2 * i + 1]) << 32) | __float_as_uint(q[2 * i]);
+      asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p fma.rn.f32x2 %0, %1, %2, %0;\n\t}"
+          : "+l"(p[i]) : "l"(qq), "l"(mm), "r"(flag));
     }
   }
 };
@@ -100,6 +123,54 @@ struct LoadPieces {
     for (int c = 0; c < NCH; ++c) lds16(addr, c * SSTEP, out + c * Vec16<T>::V);
   }
 };
+
+template <typename T, int N>
+__device__ __forceinline__ void keep_alive(const T (&q)[N]);
+template <>
+__device__ __forceinline__ void keep_alive<float, 16>(const float (&q)[16]) {
+  asm volatile("" ::"f"(q[0]), "f"(q[1]), "f"(q[2]), "f"(q[3]), "f"(q[4]), "f"(q[5]), "f"(q[6]), "f"(q[7]),
+               "f"(q[8]), "f"(q[9]), "f"(q[10]), "f"(q[11]), "f"(q[12]), "f"(q[13]), "f"(q[14]), "f"(q[15]));
+}
+template <typename T, int N>
+__device__ __forceinline__ void keep_alive(const T (&)[N]) {}
+
+// One streamed row applied to the fields of the R trajectories of a CTA.  bit: the site of the row
+// within its block (one bit set); am[r] / sm[r]: accept and sign masks of the block (see apply_rows).
+// The trajectories are handled in groups of G: a group is skipped with one uniform branch when none
+// of its members flipped the site.  OSA_APPLY_VARIANT 0: every member of an active group runs
+// h += m * q with m in {-1, 0, +1}; 1: one more uniform branch per member, no FMAs with m = 0.
+template <typename T, int NCH, int R, int G>
+__device__ __forceinline__ void apply_row(uint32_t bit, const uint32_t (&am)[R], const uint32_t (&sm)[R],
+                                          const T (&qv)[NCH * Vec16<T>::V],
+                                          Field<T, NCH * Vec16<T>::V> (&h)[R]) {
+  static_assert(R % G == 0, "R must be a multiple of the group size");
+#pragma unroll
+  for (int gg = 0; gg < R / G; ++gg) {
+#ifdef OSA_APPLY_REVERSE
+    const int g = R / G - 1 - gg;
+#else
+    const int g = gg;
+#endif
+    uint32_t gm = 0u;
+#pragma unroll
+    for (int k = 0; k < G; ++k) gm |= am[g * G + k];
+    if (gm & bit) {
+#pragma unroll
+      for (int k = 0; k < G; ++k) {
+        const int r = g * G + k;
+#if OSA_APPLY_VARIANT == 1
+        if (am[r] & bit) h[r].axpy((sm[r] & bit) ? (T)-1 : (T)1, qv);
+#else
+        const T m = (am[r] & ~sm[r] & bit) ? (T)1 : ((sm[r] & bit) ? (T)-1 : (T)0);  // sm is a subset of am
+        h[r].axpy(m, qv);
+#endif
+      }
+    }
+  }
+  // keep the row alive past the last FMA: otherwise the FMAs of the last trajectory are allocated
+  // onto the registers of the row and moved back to those of the field afterwards
+  keep_alive<T, NCH * Vec16<T>::V>(qv);
+}
 
 // P2: stream the rows of block i0 whose site was accepted by at least one trajectory
 // and apply them.  am[r] bit s: trajectory r flipped site i0+s; sm[r] bit s: the spin
@@ -213,8 +284,14 @@ __device__ __forceinline__ uint32_t apply_rows(const T *__restrict__ qoff, unsig
 #pragma unroll
         for (int k = 0; k < G; ++k) {
           const int r = g * G + k;
+#if OSA_APPLY_VARIANT == 1    // one branch per member: no FMAs with a zero multiplier
+          if (am[r] & bit) h[r].axpy((neg[r] & bit) ? (T)-1 : (T)1, qv);
+#elif OSA_APPLY_VARIANT == 2  // predicated members: no FMAs with a zero multiplier, no branch
+          h[r].axpy_if(am[r] & bit, (neg[r] & bit) ? (T)-1 : (T)1, qv);
+#else
           const T m = (pos[r] & bit) ? (T)1 : ((neg[r] & bit) ? (T)-1 : (T)0);
           h[r].axpy(m, qv);
+#endif
         }
       }
     }

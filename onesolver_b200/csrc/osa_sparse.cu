@@ -321,10 +321,7 @@ cudaError_t launch_impl(const SparseParams<T> &p, cudaStream_t s, LaunchInfo *in
   const size_t per_warp = sp_per_warp_bytes<T>(p.n);
   SparseParams<T> pp = p;
   pp.log_base = (size_t)((p.num_tries + 31) / 32) * (size_t)p.n;  // words; see sparse_ws_words
-  {
-    const char *e = getenv("OSA_SP_DEBUG");
-    pp.debug_flags = e ? atoi(e) : 0;
-  }
+  pp.debug_flags = probe_env_int("OSA_SP_DEBUG");  // timing experiments (probe builds only)
   const int wpb = pick_wpb(per_warp, p.num_tries, sms);
   if (wpb < 1) return cudaErrorInvalidValue;
   const size_t smem = (size_t)wpb * per_warp;

@@ -77,6 +77,53 @@ if "dbg" in what:
         run_dense(1024, capi.SWEEP_F64, 148 * 16, 8, 0.3 * 32, 0.02 * 32, "dbg%s_1024_f64" % flags)
     os.environ.pop("OSA_WS_DEBUG")
 
+if "dense4k" in what:  # the N = 4096 fp32 one-wave probes alone (A/B runs of apply-loop variants)
+    s = np.sqrt(4096)
+    run_dense(4096, capi.SWEEP_F32, 148 * 12, 4, 0.3 * s, 0.02 * s, "dense4096_f32_1wave_hot2cold")
+    run_dense(4096, capi.SWEEP_F32, 148 * 12, 4, 0.01 * s, 0.002 * s, "dense4096_f32_cold")
+    run_dense(4096, capi.SWEEP_F32, 148 * 12, 4, 2 * s, 1 * s, "dense4096_f32_hot")
+
+if "dens" in what:
+    # apply warps alone (debug flag 2) on pseudo-random masks of density 3/16, 1/16, 1/32, 1/64 per
+    # trajectory: cost of a block as a function of the rows it streams (fixed cost per block vs per row)
+    import os
+    s = np.sqrt(4096)
+    for flags in ("2", "66", "130", "194"):
+        os.environ["OSA_WS_DEBUG"] = flags
+        run_dense(4096, capi.SWEEP_F32, 148 * 12, 4, 0.3 * s, 0.02 * s, "dens%s_4096" % flags)
+    os.environ.pop("OSA_WS_DEBUG")
+
+if "flowdbg" in what:
+    # role experiments of the free-running kernel (probe builds): 1 = decide warps alone,
+    # 2 / 66 / 130 / 194 = apply warps alone on masks of density 3/16, 1/16, 1/32, 1/64
+    import os
+    s = np.sqrt(4096)
+    os.environ["OSA_WS_DEBUG"] = "1"
+    run_dense(4096, capi.SWEEP_F32, 148 * 12, 4, 0.3 * s, 0.02 * s, "flowdbg1_hot2cold")
+    run_dense(4096, capi.SWEEP_F32, 148 * 12, 4, 0.01 * s, 0.002 * s, "flowdbg1_cold")
+    run_dense(4096, capi.SWEEP_F32, 148 * 12, 4, 2 * s, 1 * s, "flowdbg1_hot")
+    for flags in ("2", "66", "130", "194"):
+        os.environ["OSA_WS_DEBUG"] = flags
+        run_dense(4096, capi.SWEEP_F32, 148 * 12, 4, 0.3 * s, 0.02 * s, "flowdbg%s" % flags)
+    os.environ.pop("OSA_WS_DEBUG")
+
+if "benchlike" in what:
+    # the bench's schedule on 2 waves of trajectories
+    tries = 148 * 12 * 2
+    q = gen.dense_uniform_qubo(4096, seed=2029)
+    with Problem.dense(q, sweep_precision=capi.SWEEP_F32) as prob:
+        sched = geo(32, 1.28, 19.2)
+        for rep in range(2):
+            res = prob.anneal(sched, 32, tries, mode=capi.MODE_SEQUENTIAL_SWEEP)
+        st = res.stats
+    sec = st["ms_sweep"] * 1e-3
+    gbs = (st["row_fetches"] + st["init_row_fetches"]) * 16384 / sec / 1e9
+    print(json.dumps({"probe": "benchlike_4096_f32", "tries": tries, "ms_sweep": round(st["ms_sweep"], 3),
+                      "attempts_per_s": st["attempts"] / sec, "accept_frac": st["accepts"] / st["attempts"],
+                      "row_gbs": gbs, "frac_of_18223": gbs / 18223.7,
+                      "kcyc_per_cta": {k: round(st[k] / max(1, st["grid"]) / 1e3, 1)
+                                       for k in ("cyc_init", "cyc_stage", "cyc_decide", "cyc_apply")}}))
+
 if "cfg" in what:
     import os
     s = np.sqrt(4096)
