@@ -11,6 +11,7 @@
 #include <iostream>
 #include <memory>
 #include <string>
+#include <vector>
 
 #include "cli_options.hpp"
 #include "helpers/devices.hpp"
@@ -71,11 +72,13 @@ inline qubo::QUBOModel<int, double> read_model(const std::string &path) {
   return qubo::QUBOModel<int, double>::load(file);
 }
 
-// the reference prints the first line and then dereferences a null queue; we stop instead
-inline std::unique_ptr<devices::queue> open_device(const std::string &type, int gpu_index = 0) {
+// the reference prints the first line and then dereferences a null queue; we stop instead.
+// gpu_devices: the CUDA devices of a "gpu" queue (empty: every visible one)
+inline std::unique_ptr<devices::queue> open_device(const std::string &type,
+                                                   const std::vector<int> &gpu_devices) {
   try {
     std::unique_ptr<devices::queue> q(
-        new devices::queue(*devices::construct_device_selector(type), gpu_index));
+        new devices::queue(*devices::construct_device_selector(type), gpu_devices));
     std::cout << "Using device: " << q->device_name() << std::endl;
     return q;
   } catch (const std::runtime_error &e) {
@@ -83,6 +86,9 @@ inline std::unique_ptr<devices::queue> open_device(const std::string &type, int 
     std::cerr << "error: " << e.what() << "\n";
     throw Exit{kExitError};
   }
+}
+inline std::unique_ptr<devices::queue> open_device(const std::string &type, int gpu_index = 0) {
+  return open_device(type, std::vector<int>{gpu_index});
 }
 
 // main() body wrapper: maps Exit and exceptions to the reference's exit codes

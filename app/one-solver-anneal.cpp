@@ -7,7 +7,9 @@
 // --device-type (host); exit 0 on success/help, -1 on bad arguments or an unreadable input,
 // 1 on an exception.  Extra flags (all optional, defaults keep the reference behaviour):
 // --mode random|sweep, --accept reference|boltzmann, --sweeps-per-beta, --seed,
-// --precision f64|f32, --layout auto|dense|csr, --gpu-index, --stats; --algorithm sa|pt with
+// --precision f64|f32, --layout auto|dense|csr, --stats; --gpu-index K (one CUDA device) or
+// --num-gpus G (devices 0..G-1) -- without either, --device-type gpu uses every visible GPU and
+// shards the trajectories over them (osa_multi_anneal); --algorithm sa|pt with
 // --num-replicas: parallel tempering (GPU only) -- the beta range becomes a ladder of
 // --num-replicas temperatures (built by the chosen schedule type), --num-iter counts rounds,
 // --sweeps-per-beta the sweeps per round and --num-tries the independent ladders.
@@ -23,7 +25,8 @@ namespace {
 struct Settings {
   std::string input_file, output_file, schedule_type, device_type, algorithm;
   unsigned int num_iter = 0, num_tries = 0, num_replicas = 0;
-  int sweeps_per_beta = 1, gpu_index = 0;
+  int sweeps_per_beta = 1;
+  std::vector<int> gpu_devices;  // empty: every visible GPU
   double beta_min = 0.0, beta_max = 0.0;
   bool print_stats = false;
   sa::Options engine;
@@ -43,7 +46,8 @@ void declare_options(cli::Options &options) {
       .add("seed", true, "1234", "random seed")
       .add("precision", true, "f64", "sweep arithmetic on the gpu: f64 or f32")
       .add("layout", true, "auto", "gpu problem layout: auto, dense or csr")
-      .add("gpu-index", true, "0", "CUDA device to use with --device-type gpu")
+      .add("gpu-index", true, "", "use this CUDA device only (default: every visible GPU)")
+      .add("num-gpus", true, "", "use CUDA devices 0..N-1 (default: every visible GPU)")
       .add("stats", false, "", "print engine statistics (gpu)")
       .add("algorithm", true, "sa", "sa (simulated annealing) or pt (parallel tempering, gpu)")
       .add("num-replicas", true, "12", "temperatures per ladder with --algorithm pt");
@@ -83,7 +87,15 @@ Settings read_settings(const cli::Options &options) {
                                     : (layout == "dense" ? sa::Layout::dense : sa::Layout::automatic);
   s.engine.seed = options.uint("seed");
   s.sweeps_per_beta = static_cast<int>(options.uint("sweeps-per-beta"));
-  s.gpu_index = static_cast<int>(options.uint("gpu-index"));
+  if (options.count("gpu-index") && options.count("num-gpus"))
+    cli::usage_error("Give either --gpu-index or --num-gpus, not both");
+  if (options.count("gpu-index")) s.gpu_devices = {static_cast<int>(options.uint("gpu-index"))};
+  if (options.count("num-gpus")) {
+    const int g = static_cast<int>(options.uint("num-gpus"));
+    if (g < 1) cli::usage_error("--num-gpus must be at least 1");
+    for (int d = 0; d < g; ++d) s.gpu_devices.push_back(d);
+  }
+  if (s.algorithm == "pt" && s.gpu_devices.empty()) s.gpu_devices = {0};  // one device per ladder set
   s.print_stats = options.count("stats");
   return s;
 }
@@ -110,7 +122,7 @@ int main(int argc, char *argv[]) {
     print_banner(s);
 
     const auto instance = cli::read_model(s.input_file);
-    const auto device = cli::open_device(s.device_type, s.gpu_index);
+    const auto device = cli::open_device(s.device_type, s.gpu_devices);
 
     // simulated annealing: one beta per iteration; parallel tempering: one beta per replica
     const bool tempering = s.algorithm == "pt";
@@ -138,6 +150,7 @@ int main(int argc, char *argv[]) {
                 << ", accepts " << stats.accepts << ", row fetches " << stats.row_fetches
                 << ", device ms " << stats.ms_total << " (sweep " << stats.ms_sweep << ", energy "
                 << stats.ms_energy << ")" << std::endl;
+      if (stats.reserved > 1) std::cout << "Devices: " << stats.reserved << std::endl;
       if (tempering) std::cout << "Replica exchanges accepted: " << stats.pt_swaps << std::endl;
     }
   });

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define OSA_ABI_VERSION 2
+#define OSA_ABI_VERSION 3
 
 typedef enum {
   OSA_OK = 0,
@@ -150,6 +150,31 @@ typedef struct osa_pt_params {
 int osa_pt_anneal(osa_problem *p, const double *betas, const osa_pt_params *params,
                   double *best_energies, uint32_t *best_states_packed, uint8_t *best_state,
                   double *best_energy, uint64_t *best_index, osa_stats *stats);
+
+/* ---- the same call sharded over the GPUs of one box (BASELINE config 5: 1M tries over 8 B200).
+ * One process, one host thread and stream per GPU, Q replicated, device k of G runs the global
+ * trajectory ids of shard k (contiguous ranges, remainder to the low devices); the random streams
+ * are keyed by global ids, so every output is identical to the one-device call.  The only
+ * exchange is ONE ncclAllGather of {best energy, global id, packed best state} per device at the
+ * end; the winner is min energy, then min id (std::min_element, annealing.hpp:134).
+ * devices: CUDA ordinals, or NULL for devices 0..num_devices-1 (num_devices <= 0: all visible).
+ * stats: sums over the devices, times = the slowest device, reserved = number of devices;
+ * device_stats[number of devices] (may be NULL): the per-device records.                        */
+typedef struct osa_multi osa_multi;
+int osa_multi_create_dense_f64(const double *qsym, int n, const int *devices, int num_devices,
+                               int sweep_precision, osa_multi **out);
+int osa_multi_create_dense_f32(const float *qsym, int n, const int *devices, int num_devices,
+                               osa_multi **out);
+int osa_multi_create_csr_f64(const int32_t *rowptr, const int32_t *col, const double *val,
+                             const double *diag, int n, const int *devices, int num_devices,
+                             int sweep_precision, osa_multi **out);
+int osa_multi_destroy(osa_multi *m);
+int osa_multi_devices(const osa_multi *m, int *num_devices, int *devices, int capacity);
+int osa_multi_problem(osa_multi *m, int slot, osa_problem **out); /* the replica on device slot */
+int osa_multi_anneal(osa_multi *m, const double *beta_schedule, const osa_anneal_params *params,
+                     double *best_energies, uint32_t *best_states_packed, uint8_t *best_state,
+                     double *best_energy, uint64_t *best_index, osa_stats *stats,
+                     osa_stats *device_stats);
 
 /* sa::energy (annealing.hpp:31-40) for a batch of packed states, fp64 on the device */
 int osa_energy_batch(osa_problem *p, const uint32_t *states_packed, uint64_t count, double *out);

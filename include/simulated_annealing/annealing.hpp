@@ -12,10 +12,16 @@
 // engine adds (sequential-sweep mode, Boltzmann rule, fp32 sweep arithmetic, CSR layout,
 // seed, shard offset); its defaults reproduce the reference's behaviour: random-site
 // attempts, acceptance exp((E_cur - E_new) / beta) > u, seed 1234, fp64.
+// A queue that holds several CUDA devices (the default of "gpu": every visible one) makes the
+// call shard the trajectories over them (osa_multi_anneal: one host thread and stream per GPU, Q
+// replicated, one NCCL all-gather of the best records); the result does not depend on the
+// number of devices.
 #ifndef ONESOLVER_B200_SA_ANNEALING_HPP_
 #define ONESOLVER_B200_SA_ANNEALING_HPP_
 
 #include <algorithm>
+#include <atomic>
+#include <cmath>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
@@ -53,6 +59,9 @@ struct Options {
   std::uint64_t first_try = 0;
   Layout layout = Layout::automatic;
   osa_stats *stats = nullptr;  // filled on the GPU path when non-null
+  // a GPU takes part in a multi-device call only if its shard has at least this many
+  // trajectories (a shard smaller than one wave of CTAs gains nothing from another device)
+  std::uint64_t min_tries_per_device = 2048;
 };
 
 namespace detail {
@@ -65,7 +74,11 @@ inline void check(int rc, const char *what) {
 
 struct ProblemGuard {
   osa_problem *p = nullptr;
-  ~ProblemGuard() { osa_problem_destroy(p); }
+  osa_multi *m = nullptr;
+  ~ProblemGuard() {
+    osa_problem_destroy(p);
+    osa_multi_destroy(m);
+  }
 };
 
 inline std::vector<double> threshold_scale(const std::vector<double> &beta, int num_iter,
@@ -88,8 +101,20 @@ qubo::Solution anneal(qubo::QUBOModel<int, T> instance, devices::queue q,
     throw std::invalid_argument("anneal: num_iter must be in [1, beta_schedule.size()]");
   if (num_tries == 0) throw std::invalid_argument("anneal: num_tries must be positive");
 
+  // one validation for every device type (the C ABI applies the same rule)
+  for (int i = 0; i < num_iter; ++i)
+    if (!(h_beta_schedule[i] > 0.0) || !std::isfinite(h_beta_schedule[i]))
+      throw std::invalid_argument("anneal: beta_schedule[" + std::to_string(i) +
+                                  "] is not a positive finite number");
+
   if (q.is_gpu()) {
     detail::ProblemGuard guard;
+    // devices that take part: as many of the queue's GPUs as there are shards worth having
+    const std::uint64_t per = opt.min_tries_per_device ? opt.min_tries_per_device : 1;
+    std::vector<int> devs(q.cuda_devices());
+    const std::size_t want = static_cast<std::size_t>(std::max<std::uint64_t>(1, num_tries / per));
+    if (devs.size() > want) devs.resize(want);
+    const bool multi = devs.size() > 1;
     const double density =
         static_cast<double>(instance.quadratic_terms().size()) * 2.0 / (static_cast<double>(N) * N);
     const bool use_csr = opt.layout == Layout::csr ||
@@ -100,16 +125,29 @@ qubo::Solution anneal(qubo::QUBOModel<int, T> instance, devices::queue q,
       for (const auto &t : instance.linear_terms()) as_double.add_variable(t.first, t.second);
       for (const auto &t : instance.quadratic_terms()) as_double.add_connection(t.first, t.second);
       const auto csr = helpers::build_csr(as_double);
-      detail::check(osa_problem_create_csr_f64(csr.rowptr.data(), csr.col.data(), csr.val.data(),
-                                               csr.diag.data(), N, q.cuda_device(),
-                                               opt.sweep_precision, &guard.p),
-                    "osa_problem_create_csr_f64");
+      if (multi)
+        detail::check(osa_multi_create_csr_f64(csr.rowptr.data(), csr.col.data(), csr.val.data(),
+                                               csr.diag.data(), N, devs.data(),
+                                               static_cast<int>(devs.size()), opt.sweep_precision,
+                                               &guard.m),
+                      "osa_multi_create_csr_f64");
+      else
+        detail::check(osa_problem_create_csr_f64(csr.rowptr.data(), csr.col.data(), csr.val.data(),
+                                                 csr.diag.data(), N, devs[0], opt.sweep_precision,
+                                                 &guard.p),
+                      "osa_problem_create_csr_f64");
     } else {
       const auto flat = helpers::flatten_qubo(instance);
       std::vector<double> flat64(flat.begin(), flat.end());
-      detail::check(osa_problem_create_dense_f64(flat64.data(), N, q.cuda_device(),
-                                                 opt.sweep_precision, &guard.p),
-                    "osa_problem_create_dense_f64");
+      if (multi)
+        detail::check(osa_multi_create_dense_f64(flat64.data(), N, devs.data(),
+                                                 static_cast<int>(devs.size()),
+                                                 opt.sweep_precision, &guard.m),
+                      "osa_multi_create_dense_f64");
+      else
+        detail::check(osa_problem_create_dense_f64(flat64.data(), N, devs[0], opt.sweep_precision,
+                                                   &guard.p),
+                      "osa_problem_create_dense_f64");
     }
     osa_anneal_params prm{};
     prm.seed = opt.seed;
@@ -122,14 +160,22 @@ qubo::Solution anneal(qubo::QUBOModel<int, T> instance, devices::queue q,
     std::vector<std::uint8_t> state(N);
     double best_energy = 0.0;
     std::uint64_t best_index = 0;
-    detail::check(osa_anneal(guard.p, h_beta_schedule.data(), &prm, nullptr, nullptr, state.data(),
-                             &best_energy, &best_index, opt.stats),
-                  "osa_anneal");
+    if (multi)
+      detail::check(osa_multi_anneal(guard.m, h_beta_schedule.data(), &prm, nullptr, nullptr,
+                                     state.data(), &best_energy, &best_index, opt.stats, nullptr),
+                    "osa_multi_anneal");
+    else
+      detail::check(osa_anneal(guard.p, h_beta_schedule.data(), &prm, nullptr, nullptr,
+                               state.data(), &best_energy, &best_index, opt.stats),
+                    "osa_anneal");
     return qubo::Solution(state.begin(), state.end(), best_energy);
   }
 
   // ---- "cpu" / "host" device types: the host engine, trajectories spread over threads
   if (sweeps_per_beta <= 0) throw std::invalid_argument("anneal: sweeps_per_beta must be positive");
+  if (opt.sweep_precision != OSA_SWEEP_F64)
+    throw std::invalid_argument("anneal: fp32 sweep arithmetic runs on the gpu device type only "
+                                "(the host engine computes in fp64)");
   const auto flat = helpers::flatten_qubo(instance);
   std::vector<double> qsym(flat.begin(), flat.end()), qoff(qsym), diag(N);
   for (int i = 0; i < N; ++i) {

@@ -6,6 +6,7 @@ csrc/).  The Python modules here only drive it from pytest and bench.py.
 from . import capi  # noqa: F401
 from .anneal import (  # noqa: F401
     AnnealResult,
+    MultiProblem,
     Problem,
     construct_geometric_beta_schedule,
     construct_linear_beta_schedule,

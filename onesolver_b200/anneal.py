@@ -71,6 +71,7 @@ class Problem:
         val = np.ascontiguousarray(val, dtype=np.float64)
         diag = np.ascontiguousarray(diag, dtype=np.float64)
         n = diag.shape[0]
+        _check_csr_lengths(rowptr, col, val, n)
         h = ctypes.c_void_p()
         capi.check(lib.osa_problem_create_csr_f64(rowptr.ctypes.data, col.ctypes.data,
                                                   val.ctypes.data, diag.ctypes.data, n, device,
@@ -154,6 +155,115 @@ class Problem:
         out = np.empty(s.shape[0], dtype=np.float64)
         capi.check(lib.osa_energy_batch(self._h, s.ctypes.data, s.shape[0], out.ctypes.data))
         return out
+
+
+def _check_csr_lengths(rowptr, col, val, n):
+    """The C side reads rowptr[0..n] and col/val[0..rowptr[n]): check the array lengths first."""
+    if rowptr.ndim != 1 or rowptr.shape[0] != n + 1:
+        raise ValueError(f"rowptr must have n + 1 = {n + 1} entries (got {rowptr.shape})")
+    nnz = int(rowptr[n])
+    if nnz < 0 or col.shape[0] < nnz or val.shape[0] < nnz:
+        raise ValueError(f"col/val shorter than rowptr[n] = {nnz}")
+
+
+class MultiProblem:
+    """Q replicated on several GPUs of one box (osa_multi_*): one process, one host thread and
+    stream per GPU, trajectories sharded by global id, one NCCL all-gather of the best records."""
+
+    def __init__(self, handle, n):
+        self._h = handle
+        self.n = n
+        self.nw = (n + 31) // 32
+        c = ctypes.c_int()
+        capi.check(capi.load().osa_multi_devices(self._h, ctypes.byref(c), None, 0))
+        self.num_devices = c.value
+
+    @staticmethod
+    def _devices(devices, num_devices):
+        if devices is None:
+            return None, int(num_devices or 0)
+        d = np.ascontiguousarray(devices, dtype=np.int32)
+        return d, int(d.shape[0])
+
+    @classmethod
+    def dense(cls, qsym, devices=None, num_devices=0, sweep_precision=capi.SWEEP_F64):
+        lib = capi.load()
+        q = np.ascontiguousarray(qsym)
+        if q.ndim != 2 or q.shape[0] != q.shape[1]:
+            raise ValueError("qsym must be a square matrix")
+        d, nd = cls._devices(devices, num_devices)
+        h = ctypes.c_void_p()
+        if q.dtype == np.float32:
+            capi.check(lib.osa_multi_create_dense_f32(q.ctypes.data, q.shape[0],
+                                                      d.ctypes.data if d is not None else None, nd,
+                                                      ctypes.byref(h)))
+        else:
+            q = np.ascontiguousarray(q, dtype=np.float64)
+            capi.check(lib.osa_multi_create_dense_f64(q.ctypes.data, q.shape[0],
+                                                      d.ctypes.data if d is not None else None, nd,
+                                                      sweep_precision, ctypes.byref(h)))
+        return cls(h, q.shape[0])
+
+    @classmethod
+    def csr(cls, rowptr, col, val, diag, devices=None, num_devices=0,
+            sweep_precision=capi.SWEEP_F64):
+        lib = capi.load()
+        rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+        col = np.ascontiguousarray(col, dtype=np.int32)
+        val = np.ascontiguousarray(val, dtype=np.float64)
+        diag = np.ascontiguousarray(diag, dtype=np.float64)
+        n = diag.shape[0]
+        _check_csr_lengths(rowptr, col, val, n)
+        d, nd = cls._devices(devices, num_devices)
+        h = ctypes.c_void_p()
+        capi.check(lib.osa_multi_create_csr_f64(rowptr.ctypes.data, col.ctypes.data, val.ctypes.data,
+                                                diag.ctypes.data, n,
+                                                d.ctypes.data if d is not None else None, nd,
+                                                sweep_precision, ctypes.byref(h)))
+        return cls(h, n)
+
+    def close(self):
+        if self._h:
+            capi.load().osa_multi_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def anneal(self, beta_schedule, num_iter, num_tries, sweeps_per_beta=1, seed=1234,
+               first_try=0, mode=capi.MODE_RANDOM_SITE, accept_rule=capi.ACCEPT_REFERENCE,
+               kernel_variant=capi.KID_AUTO, want_energies=False, want_states=False):
+        lib = capi.load()
+        sched = np.ascontiguousarray(beta_schedule, dtype=np.float64)
+        if sched.shape[0] < num_iter:
+            raise ValueError("beta_schedule shorter than num_iter")
+        prm = capi.AnnealParams(seed=seed, first_try=first_try, num_tries=num_tries,
+                                num_iter=num_iter, sweeps_per_beta=sweeps_per_beta, mode=mode,
+                                accept_rule=accept_rule, kernel_variant=kernel_variant, flags=0)
+        energies = np.empty(num_tries, dtype=np.float64) if want_energies else None
+        states = np.empty((num_tries, self.nw), dtype=np.uint32) if want_states else None
+        state = np.empty(self.n, dtype=np.uint8)
+        e = ctypes.c_double()
+        idx = ctypes.c_uint64()
+        st = capi.Stats()
+        per = (capi.Stats * self.num_devices)()
+        capi.check(lib.osa_multi_anneal(self._h, sched.ctypes.data, ctypes.byref(prm),
+                                        energies.ctypes.data if want_energies else None,
+                                        states.ctypes.data if want_states else None,
+                                        state.ctypes.data, ctypes.byref(e), ctypes.byref(idx),
+                                        ctypes.byref(st), ctypes.cast(per, ctypes.c_void_p)))
+        res = AnnealResult(state, e.value, idx.value, st.as_dict(), energies, states)
+        res.device_stats = [s.as_dict() for s in per]
+        return res
 
 
 def pinned_copy(array):

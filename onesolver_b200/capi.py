@@ -24,6 +24,8 @@ EXPORTED_SYMBOLS = [
     "osa_problem_create_csr_f64", "osa_problem_destroy", "osa_problem_size", "osa_anneal",
     "osa_pt_anneal", "osa_energy_batch", "osa_exhaustive_dense_f64", "osa_host_alloc_pinned",
     "osa_host_free_pinned", "osa_measure_read_bandwidth",
+    "osa_multi_create_dense_f64", "osa_multi_create_dense_f32", "osa_multi_create_csr_f64",
+    "osa_multi_destroy", "osa_multi_devices", "osa_multi_problem", "osa_multi_anneal",
 ]
 
 
@@ -122,6 +124,14 @@ def load():
     lib.osa_host_free_pinned.argtypes = [vp]
     lib.osa_exhaustive_dense_f64.argtypes = [vp, i32, i32, vp, P(ctypes.c_double)]
     lib.osa_measure_read_bandwidth.argtypes = [i32, sz, i32, P(ctypes.c_double)]
+    lib.osa_multi_create_dense_f64.argtypes = [vp, i32, vp, i32, i32, P(vp)]
+    lib.osa_multi_create_dense_f32.argtypes = [vp, i32, vp, i32, P(vp)]
+    lib.osa_multi_create_csr_f64.argtypes = [vp, vp, vp, vp, i32, vp, i32, i32, P(vp)]
+    lib.osa_multi_destroy.argtypes = [vp]
+    lib.osa_multi_devices.argtypes = [vp, P(i32), vp, i32]
+    lib.osa_multi_problem.argtypes = [vp, i32, P(vp)]
+    lib.osa_multi_anneal.argtypes = [vp, vp, P(AnnealParams), vp, vp, vp, P(ctypes.c_double), P(u64),
+                                     P(Stats), vp]
     _lib = lib
     return lib
 

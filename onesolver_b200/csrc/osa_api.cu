@@ -5,6 +5,7 @@
 // annealing.hpp:59-72), kernel selection, the exact-energy epilogue and the argmin
 // (annealing.hpp:134-139).  No CPU compute path exists here: every failure to reach a
 // CUDA device is reported as an error.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -12,9 +13,10 @@
 #include <new>
 #include <string>
 #include <limits>
+#include <mutex>
 #include <vector>
 
-#include "osa_common.cuh"
+#include "osa_internal.h"
 
 using namespace osa;
 
@@ -28,7 +30,7 @@ cudaError_t exhaustive_search(const double *qsym_host, int n, unsigned long long
 // ---------------------------------------------------------------------------
 static thread_local std::string g_last_error;
 
-static int fail(int code, const char *fmt, ...) {
+int osa_fail(int code, const char *fmt, ...) {
   char buf[512];
   va_list ap;
   va_start(ap, fmt);
@@ -37,6 +39,7 @@ static int fail(int code, const char *fmt, ...) {
   g_last_error = buf;
   return code;
 }
+#define fail osa_fail
 
 #define CUDA_TRY(expr)                                                                       \
   do {                                                                                       \
@@ -53,64 +56,46 @@ static int fail(int code, const char *fmt, ...) {
 // ---------------------------------------------------------------------------
 // problem handle
 // ---------------------------------------------------------------------------
-struct osa_problem {
-  int device = 0;
-  int n = 0;
-  int nw = 0;
-  bool sparse = false;
-  int prec = OSA_SWEEP_F64;
-  // dense
-  size_t ld = 0;          // leading dimension of qoff (sweep precision)
-  size_t rows_pad = 0;    // rows allocated (multiple of 32)
-  void *d_qoff = nullptr; // zero-diagonal symmetric copy, sweep precision
-  void *d_diag = nullptr; // [ld] sweep precision
-  size_t ld64 = 0;
-  double *d_q64 = nullptr; // [rows_pad][ld64] original values incl. diagonal (exact energies)
-  // csr
-  int64_t nnz = 0;
-  int32_t *d_rowptr = nullptr, *d_col = nullptr;
-  void *d_val = nullptr;      // sweep precision
-  double *d_val64 = nullptr;
-  double *d_diag64 = nullptr;
-  // execution
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  // workspace (grow-only)
-  size_t cap_tries = 0;
-  double *d_best_rel = nullptr;
-  double *d_energy = nullptr;
-  uint32_t *d_states = nullptr;
-  size_t cap_states_words = 0;
-  uint32_t *d_xbest_ws = nullptr;
-  size_t cap_ws_words = 0;
-  void *d_tscale = nullptr;
-  size_t cap_tscale_bytes = 0;
-  Counters *d_counters = nullptr;
-  unsigned long long *d_arg_idx = nullptr;
-  double *d_arg_e = nullptr;
-};
-
 namespace {
 
 size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
 
-// Device memory comes from the stream-ordered allocator with an unlimited release threshold, so
-// the create -> anneal -> destroy cycle of one sa::anneal call reuses pooled memory instead of
-// paying cudaMalloc/cudaFree (tens of milliseconds for the 64-128 MiB arrays) every time.
-void keep_pool_memory(int device) {
-  static bool done[64] = {false};
-  if (device < 0 || device >= 64 || done[device]) return;
-  cudaMemPool_t pool = nullptr;
-  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+// Device memory comes from a PRIVATE stream-ordered pool per device with an unlimited release
+// threshold, so the create -> anneal -> destroy cycle of one sa::anneal call reuses pooled memory
+// instead of paying cudaMalloc/cudaFree (tens of milliseconds for the 64-128 MiB arrays) every
+// time -- without touching the default pool of the host application.
+std::mutex g_pool_mutex;
+cudaMemPool_t g_pools[64] = {nullptr};
+
+cudaError_t device_pool(int device, cudaMemPool_t *out) {
+  if (device < 0 || device >= 64) return cudaErrorInvalidDevice;
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  if (!g_pools[device]) {
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    cudaMemPool_t pool = nullptr;
+    cudaError_t e = cudaMemPoolCreate(&pool, &props);
+    if (e != cudaSuccess) return e;
     unsigned long long threshold = ~0ull;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    g_pools[device] = pool;
   }
-  done[device] = true;
+  *out = g_pools[device];
+  return cudaSuccess;
 }
 
 template <typename P>
 cudaError_t dev_alloc(P **ptr, size_t bytes, cudaStream_t stream) {
-  return cudaMallocAsync(reinterpret_cast<void **>(ptr), bytes, stream);
+  int device = 0;
+  cudaError_t e = cudaGetDevice(&device);
+  cudaMemPool_t pool = nullptr;
+  if (e == cudaSuccess) e = device_pool(device, &pool);
+  if (e != cudaSuccess) return e;
+  return cudaMallocFromPoolAsync(reinterpret_cast<void **>(ptr), bytes, pool, stream);
 }
 template <typename P>
 void dev_free(P *ptr, cudaStream_t stream) {
@@ -158,7 +143,6 @@ __global__ void k_convert(const double *__restrict__ in, T *__restrict__ out, si
 int init_exec(osa_problem *p) {
   CUDA_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
   for (auto &e : p->ev) CUDA_TRY(cudaEventCreate(&e));
-  keep_pool_memory(p->device);
   CUDA_TRY(dev_alloc(&p->d_counters, sizeof(Counters), p->stream));
   CUDA_TRY(dev_alloc(&p->d_arg_idx, sizeof(unsigned long long), p->stream));
   CUDA_TRY(dev_alloc(&p->d_arg_e, sizeof(double), p->stream));
@@ -183,6 +167,7 @@ int create_dense(const TIn *qsym, int n, int device, int prec, osa_problem **out
   if (n < 1) return fail(OSA_ERR_INVALID, "n must be >= 1 (got %d)", n);
   if (prec != OSA_SWEEP_F64 && prec != OSA_SWEEP_F32)
     return fail(OSA_ERR_INVALID, "unknown sweep precision %d", prec);
+  DeviceGuard guard;
   int rc = select_device(device);
   if (rc) return rc;
 
@@ -329,6 +314,7 @@ int osa_device_count(int *count) {
 
 int osa_device_name(int device, char *buf, size_t buflen) {
   if (!buf || buflen == 0) return fail(OSA_ERR_INVALID, "null argument");
+  DeviceGuard guard;
   int rc = select_device(device);
   if (rc) return rc;
   cudaDeviceProp prop;
@@ -374,6 +360,22 @@ int osa_problem_create_csr_f64(const int32_t *rowptr, const int32_t *col, const 
         return fail(OSA_ERR_INVALID, "row %d: bad column %d", i, col[q]);
       if (q > rowptr[i] && col[q] <= col[q - 1])
         return fail(OSA_ERR_INVALID, "row %d: columns must be strictly ascending", i);
+    }
+  }
+  DeviceGuard guard;
+  // both directions of every coupling, with the same value: the sweep reads row i for the local
+  // field of i while the exact energies sum the entries with col > i, so a one-sided or
+  // asymmetric upload would make the two disagree without any error (the dense path rejects an
+  // asymmetric Q in the same way, k_check_symmetric)
+  for (int i = 0; i < n; ++i) {
+    for (int32_t q = rowptr[i]; q < rowptr[i + 1]; ++q) {
+      const int j = col[q];
+      const int32_t *lo = col + rowptr[j], *hi = col + rowptr[j + 1];
+      const int32_t *it = std::lower_bound(lo, hi, (int32_t)i);
+      if (it == hi || *it != i)
+        return fail(OSA_ERR_INVALID, "CSR is not symmetric: entry (%d, %d) has no (%d, %d)", i, j, j, i);
+      if (!(val[it - col] == val[q]))
+        return fail(OSA_ERR_INVALID, "CSR is not symmetric: value(%d, %d) != value(%d, %d)", i, j, j, i);
     }
   }
   int rc = select_device(device);
@@ -437,6 +439,7 @@ int osa_problem_create_csr_f64(const int32_t *rowptr, const int32_t *col, const 
 
 int osa_problem_destroy(osa_problem *p) {
   if (!p) return OSA_OK;
+  DeviceGuard guard;
   cudaSetDevice(p->device);
   cudaStream_t st = p->stream;
   if (p->sparse) {
@@ -496,6 +499,7 @@ int osa_anneal(osa_problem *p, const double *beta_schedule, const osa_anneal_par
       return fail(OSA_ERR_INVALID, "beta_schedule[%d] = %g is not a positive finite number", i,
                   beta_schedule[i]);
 
+  DeviceGuard guard;
   int rc = select_device(p->device);
   if (rc) return rc;
   rc = ensure_workspace(p, prm->num_tries, prm->num_iter);
@@ -687,6 +691,7 @@ int osa_pt_anneal(osa_problem *p, const double *betas, const osa_pt_params *prm,
   const uint64_t tries = prm->num_groups * (uint64_t)M;
   const uint64_t first_try = prm->first_group * (uint64_t)M;
 
+  DeviceGuard guard;
   int rc = select_device(p->device);
   if (rc) return rc;
   rc = ensure_workspace(p, tries, 1);
@@ -896,6 +901,7 @@ int osa_pt_anneal(osa_problem *p, const double *betas, const osa_pt_params *prm,
 int osa_energy_batch(osa_problem *p, const uint32_t *states_packed, uint64_t count, double *out) {
   if (!p || !states_packed || !out) return fail(OSA_ERR_INVALID, "null argument");
   if (count == 0) return OSA_OK;
+  DeviceGuard guard;
   int rc = select_device(p->device);
   if (rc) return rc;
   rc = ensure_workspace(p, count, 1);
@@ -934,6 +940,7 @@ int osa_exhaustive_dense_f64(const double *qsym, int n, int device, uint8_t *bes
     for (int j = i + 1; j < n; ++j)
       if (!(qsym[(size_t)i * n + j] == qsym[(size_t)j * n + i]))
         return fail(OSA_ERR_INVALID, "Q is not symmetric (expected helpers::flatten_qubo layout)");
+  DeviceGuard guard;
   int rc = select_device(device);
   if (rc) return rc;
   unsigned long long x = 0;
@@ -948,6 +955,7 @@ int osa_exhaustive_dense_f64(const double *qsym, int n, int device, uint8_t *bes
 
 int osa_measure_read_bandwidth(int device, size_t bytes, int iters, double *gbs) {
   if (!gbs || bytes < 16 || iters < 1) return fail(OSA_ERR_INVALID, "bad argument");
+  DeviceGuard guard;
   int rc = select_device(device);
   if (rc) return rc;
   uint4 *buf = nullptr;

@@ -10,7 +10,9 @@ import numpy as np
 
 
 def shard(num_tries, world, rank):
-    """Contiguous id range of `rank`: (first_try, count). Remainder goes to the low ranks."""
+    """Contiguous id range of `rank`: (first_try, count). Remainder goes to the low ranks.
+    count is 0 for the high ranks when num_tries < world: such a rank skips its local anneal and
+    contributes encode_best(inf, 2**64 - 1, zeros) to the gather (osa_multi_anneal does the same)."""
     base, rem = divmod(num_tries, world)
     count = base + (1 if rank < rem else 0)
     first = rank * base + min(rank, rem)
@@ -31,7 +33,10 @@ def decode_best(rows, n):
     rows = np.ascontiguousarray(rows, dtype=np.uint8)
     energies = rows[:, :8].copy().view(np.float64).ravel()
     ids = rows[:, 8:16].copy().view(np.uint64).ravel()
-    k = min(range(rows.shape[0]), key=lambda r: (energies[r], ids[r]))
+    live = [r for r in range(rows.shape[0]) if ids[r] != np.uint64(0xFFFFFFFFFFFFFFFF)]
+    if not live:
+        raise ValueError("no rank produced a result")
+    k = min(live, key=lambda r: (energies[r], ids[r]))
     state = np.unpackbits(rows[k, 16:], bitorder="little")[:n]
     return float(energies[k]), int(ids[k]), state
 

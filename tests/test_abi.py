@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert sorted(capi.EXPORTED_SYMBOLS) == names
-    assert lib.osa_abi_version() == 2
+    assert lib.osa_abi_version() == 3
 
 
 def test_struct_layouts_match_the_header():
@@ -58,3 +58,45 @@ def test_argument_validation_needs_no_device():
     assert lib.osa_problem_create_dense_f64(q.ctypes.data, 4, 0, 7, ctypes.byref(h)) == capi.OSA_ERR_INVALID
     assert lib.osa_anneal(None, None, None, None, None, None, None, None, None) == capi.OSA_ERR_INVALID
     assert lib.osa_kernel_name(1) == b"dense_seq"
+
+
+def test_multi_device_entry_has_no_cpu_fallback_either():
+    lib = capi.load()
+    c = ctypes.c_int(-1)
+    if lib.osa_device_count(ctypes.byref(c)) == 0 and c.value > 0:
+        pytest.skip("a CUDA device is present")
+    q = np.zeros((4, 4))
+    h = ctypes.c_void_p()
+    rc = lib.osa_multi_create_dense_f64(q.ctypes.data, 4, None, 0, capi.SWEEP_F64, ctypes.byref(h))
+    assert rc in (capi.OSA_ERR_NO_DEVICE, capi.OSA_ERR_CUDA) and not h.value
+    assert lib.osa_multi_anneal(None, None, None, None, None, None, None, None, None, None) == capi.OSA_ERR_INVALID
+    assert lib.osa_multi_destroy(None) == capi.OSA_OK
+
+
+def test_csr_symmetry_is_checked_before_any_device_work():
+    """An upper-triangle-only or value-asymmetric CSR is rejected (the dense path rejects an
+    asymmetric Q the same way): the sweep and the exact energies would disagree on it."""
+    lib = capi.load()
+    h = ctypes.c_void_p()
+    diag = np.zeros(3)
+    # one-sided: (0,1) without (1,0)
+    rowptr = np.array([0, 1, 1, 1], dtype=np.int32)
+    col = np.array([1], dtype=np.int32)
+    val = np.array([2.0])
+    rc = lib.osa_problem_create_csr_f64(rowptr.ctypes.data, col.ctypes.data, val.ctypes.data,
+                                        diag.ctypes.data, 3, 0, capi.SWEEP_F64, ctypes.byref(h))
+    assert rc == capi.OSA_ERR_INVALID and b"not symmetric" in lib.osa_last_error()
+    # both directions, different values
+    rowptr = np.array([0, 1, 2, 2], dtype=np.int32)
+    col = np.array([1, 0], dtype=np.int32)
+    val = np.array([2.0, 3.0])
+    rc = lib.osa_problem_create_csr_f64(rowptr.ctypes.data, col.ctypes.data, val.ctypes.data,
+                                        diag.ctypes.data, 3, 0, capi.SWEEP_F64, ctypes.byref(h))
+    assert rc == capi.OSA_ERR_INVALID and b"not symmetric" in lib.osa_last_error()
+
+
+def test_python_wrapper_checks_csr_array_lengths():
+    from onesolver_b200 import Problem
+    with pytest.raises(ValueError):
+        Problem.csr(np.array([0, 1], dtype=np.int32), np.array([1], dtype=np.int32), np.array([1.0]),
+                    np.zeros(3))

@@ -27,6 +27,19 @@ def test_encode_decode_picks_min_energy_then_lowest_id():
     assert (e, idx) == (-7.25, 1200) and (s == states[2]).all()
 
 
+def test_ranks_without_trajectories_never_win():
+    """num_tries < world: the high ranks get count 0 and contribute an infinite energy with the
+    all-ones id; decode_best ignores them."""
+    assert [multi.shard(3, 8, r)[1] for r in range(8)] == [1, 1, 1, 0, 0, 0, 0, 0]
+    n = 40
+    empty = multi.encode_best(np.inf, 2**64 - 1, np.zeros(n, dtype=np.uint8))
+    real = multi.encode_best(12.5, 2, np.ones(n, dtype=np.uint8))
+    e, idx, s = multi.decode_best(np.stack([empty, real, empty]), n)
+    assert (e, idx) == (12.5, 2) and s.all()
+    with pytest.raises(ValueError):
+        multi.decode_best(np.stack([empty, empty]), n)
+
+
 def _worker(rank, world, port, n, out_q):
     import torch
     import torch.distributed as dist
