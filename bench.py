@@ -40,7 +40,10 @@ def parse_args():
     # config5 (default) is the headline workload of BASELINE.json's metric; config3 / config4 run
     # the other GPU configs of BASELINE.json through the same timing harness (not bench lines of
     # the round: they exist so that those shapes can be measured at 1/2/4/8 GPUs as well)
-    ap.add_argument("--workload", default="config5", choices=["config5", "config3", "config4"])
+    ap.add_argument("--workload", default="config5",
+                    choices=["config5", "config3", "config4", "random_site"])
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the config3 / config4 / random-site sub-records of the headline line")
     ap.add_argument("--n", type=int, default=4096)
     ap.add_argument("--tries-per-gpu", type=int, default=131072)
     ap.add_argument("--sweeps", type=int, default=32)
@@ -82,15 +85,15 @@ class ClockSampler:
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device):
-        self.device = device
+    def __init__(self, devices):
+        self.devices = list(devices) if isinstance(devices, (list, tuple)) else [devices]
         self.lines = []
         self.proc = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
+                ["nvidia-smi", "--id=" + ",".join(str(d) for d in self.devices), f"--query-gpu={self.Q}",
                  "--format=csv,noheader,nounits", "-lms", "200"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
@@ -205,174 +208,236 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------- engine arm
+# All GPUs of the box are driven by ONE process through the product's multi-device entry
+# (osa_multi_anneal: one host thread and stream per GPU, Q replicated, trajectories sharded by global
+# id, one NCCL all-gather of the best records).  Under torchrun (the driver's launch for N > 1) rank 0
+# makes that call over devices 0..N-1; the other ranks take part in the barriers that bracket the
+# timed regions and in the max-over-ranks of the clocks, nothing else.
+class Ranks:
+    """torch.distributed plumbing of the bench contract (barrier + synchronize, max over ranks).
+
+    The ranks meet on a gloo (CPU) group: an NCCL barrier posted early by an idle rank is a kernel
+    that spins on its GPU until the last rank arrives, and the GPU then time-slices between that
+    process and rank 0's annealing kernels on the same device (measured: 2.25x slower).  The NCCL
+    process group is still created and exercised once before the timed regions."""
+
+    def __init__(self):
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.dist = self.torch = self.cpu_group = None
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist
+            torch.cuda.set_device(self.local_rank)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            t = torch.ones(1, device="cuda")
+            dist.all_reduce(t)  # one collective over NVLink: every rank is up and sees its GPU
+            torch.cuda.synchronize()
+            assert int(t.item()) == self.world
+            self.cpu_group = dist.new_group(backend="gloo")
+            self.dist, self.torch = dist, torch
+        self.active = self.rank == 0
+
+    def barrier(self):
+        if self.dist is not None:
+            self.torch.cuda.synchronize()
+            self.dist.barrier(group=self.cpu_group)
+            self.torch.cuda.synchronize()
+
+    def max(self, x):
+        if self.dist is None:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.cpu_group)
+        return float(t.item())
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.barrier(group=self.cpu_group)
+            self.dist.destroy_process_group()
+
+
+def nccl_log_setup():
+    """NCCL's own log of the library's communicator (ncclCommInitAll over the N devices): kept on,
+    in a file when the caller did not ask for it on the console."""
+    if "NCCL_DEBUG" not in os.environ:
+        os.environ["NCCL_DEBUG"] = "INFO"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/osa_bench_nccl_%h_%p.log")
+    return os.environ.get("NCCL_DEBUG_FILE")
+
+
+def nccl_log_summary(path_pattern):
+    """nranks of the communicators this process created, from NCCL's log file (None: console)."""
+    if not path_pattern:
+        return None
+    import glob
+    import re
+    import socket
+    path = path_pattern.replace("%h", socket.gethostname()).replace("%p", str(os.getpid()))
+    ranks = set()
+    for f in glob.glob(path):
+        try:
+            for line in open(f, errors="replace"):
+                m = re.search(r"nranks (\d+)", line)
+                if m:
+                    ranks.add(int(m.group(1)))
+        except OSError:
+            pass
+    return sorted(ranks)
+
+
+def measure(ranks, make_problem, sched, sweeps, total_tries, steps, warmup, mode, e2e_make=None):
+    """W warm-up calls, then K timed calls of the multi-device anneal on the resident problem,
+    bracketed by barrier + synchronize; optionally the same through host buffers (create + anneal
+    + destroy per step).  Returns a dict on every rank (timings are max over ranks)."""
+    out = {}
+    prob = make_problem() if ranks.active else None
+    agg = {"attempts": 0, "accepts": 0, "row_fetches": 0, "init_row_fetches": 0, "launches": 0,
+           "ms_total": 0.0, "ms_sweep": 0.0, "ms_energy": 0.0}
+    last = None
+    if ranks.active:
+        for _ in range(warmup):
+            prob.anneal(sched, sweeps, total_tries, mode=mode)
+    ranks.barrier()
+    t0 = time.perf_counter()
+    if ranks.active:
+        for _ in range(steps):
+            last = prob.anneal(sched, sweeps, total_tries, mode=mode)
+            for k in agg:
+                agg[k] += last.stats[k]
+    ranks.barrier()
+    out["wall_ms"] = ranks.max((time.perf_counter() - t0) * 1e3)
+    out["agg"], out["last"] = agg, last
+    if ranks.active:
+        prob.close()
+    if e2e_make is not None:
+        def e2e_step():
+            with e2e_make() as p2:  # host arrays -> device layouts on every GPU, every step
+                p2.anneal(sched, sweeps, total_tries, mode=mode, want_energies=True)
+        if ranks.active:
+            e2e_step()  # warm-up (allocator, communicator)
+        ranks.barrier()
+        t1 = time.perf_counter()
+        if ranks.active:
+            for _ in range(steps):
+                e2e_step()
+        ranks.barrier()
+        out["e2e_ms"] = ranks.max((time.perf_counter() - t1) * 1e3)
+    return out
+
+
 def run_engine(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.gpus > 1 and world == 1:
         # convenience: relaunch under torchrun, one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
                f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port",
                "29533", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
+    nccl_log = nccl_log_setup()
+    ranks = Ranks()  # (imports torch first when N > 1: one libnccl per process, see osa_multi.cu)
 
-    from onesolver_b200 import Problem, capi, measure_read_bandwidth, device_name
+    from onesolver_b200 import MultiProblem, capi, measure_read_bandwidth, device_name
 
-    dist = None
-    torch = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-            torch.cuda.synchronize()
-
+    devices = list(range(world))
     q = make_instance(args.n)
     sched = make_schedule(args)
     prec = capi.SWEEP_F32 if args.precision == "f32" else capi.SWEEP_F64
     esz = 4 if args.precision == "f32" else 8
-    tries = args.tries_per_gpu
-    first_try = rank * tries
+    tries = args.tries_per_gpu * world  # weak scaling: every GPU anneals tries_per_gpu trajectories
     mode = capi.MODE_SEQUENTIAL_SWEEP
 
-    prob = Problem.dense(q, device=local_rank, sweep_precision=prec)  # inputs resident in HBM
-
-    def reduce_best(res):
-        """Best-energy/argmin gather: one NCCL collective of (energy, id, packed state)."""
-        if dist is None:
-            return res.energy, res.index
-        from onesolver_b200.multi import gather_best
-        e, idx, _ = gather_best(dist, torch, res.energy, res.index, res.state,
-                                torch.device("cuda", local_rank))
-        return e, idx
-
-    def step():
-        res = prob.anneal(sched, args.sweeps, tries, first_try=first_try, mode=mode)
-        e, idx = reduce_best(res)
-        return res.stats, e, idx
-
-    for _ in range(args.warmup):
-        step()
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    sampler = ClockSampler(devices)
+    if ranks.active:
         sampler.start()
-    barrier()
-    t0 = time.perf_counter()
-    dev_ms = 0.0
-    sweep_ms = 0.0
-    energy_ms = 0.0
-    agg = {"attempts": 0, "accepts": 0, "row_fetches": 0, "init_row_fetches": 0, "launches": 0}
-    last = None
-    for _ in range(args.steps):
-        st, e, idx = step()
-        dev_ms += st["ms_total"]
-        sweep_ms += st["ms_sweep"]
-        energy_ms += st["ms_energy"]
-        for k in agg:
-            agg[k] += st[k]
-        last = (st, e, idx)
-    barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    clocks = sampler.stop() if rank == 0 else None
-
-    # ---- end-to-end through the C ABI with HOST buffers: upload Q, anneal, read results back
-    e2e_ms = None
-    if not args.no_e2e:
+    e2e_make = None
+    free_pinned = None
+    if not args.no_e2e and ranks.active:
         from onesolver_b200 import pinned_copy
         q_pinned, free_pinned = pinned_copy(q)  # the step's input lives in pinned host memory
-
-        def e2e_step():
-            with Problem.dense(q_pinned, device=local_rank, sweep_precision=prec) as p2:
-                r = p2.anneal(sched, args.sweeps, tries, first_try=first_try, mode=mode,
-                              want_energies=True)
-                reduce_best(r)
-        e2e_step()  # warm-up (allocator, module load)
-        barrier()
-        t1 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
-        barrier()
-        e2e_ms = (time.perf_counter() - t1) * 1e3
+        e2e_make = lambda: MultiProblem.dense(q_pinned, devices=devices, sweep_precision=prec)  # noqa: E731
+    elif not args.no_e2e:
+        e2e_make = lambda: None  # noqa: E731  (inactive ranks only keep the barriers in step)
+    m = measure(ranks, lambda: MultiProblem.dense(q, devices=devices, sweep_precision=prec), sched,
+                args.sweeps, tries, args.steps, args.warmup, mode, e2e_make)
+    clocks = sampler.stop() if ranks.active else None
+    if free_pinned:
         free_pinned()
+    # the same through a pageable std::vector-like host buffer (what a caller of sa::anneal has);
+    # a few steps are enough for this side figure
+    pageable = None
+    pageable_steps = min(args.steps, 3)
+    if not args.no_e2e and world == 1:
+        t1 = time.perf_counter()
+        for _ in range(pageable_steps):
+            with MultiProblem.dense(q, devices=devices, sweep_precision=prec) as p2:
+                p2.anneal(sched, args.sweeps, tries, mode=mode, want_energies=True)
+        pageable = (time.perf_counter() - t1) * 1e3
 
-    # ---- max over ranks
-    def rank_max(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    others = []
+    if not args.no_other_configs:
+        for name in ("config3", "config4", "random_site"):
+            others.append(run_sub_record(ranks, args, name, devices))
 
-    dev_ms = rank_max(dev_ms)
-    wall_ms = rank_max(wall_ms)
-    sweep_ms_max = rank_max(sweep_ms)
-    if e2e_ms is not None:
-        e2e_ms = rank_max(e2e_ms)
-
-    if rank == 0:
-        st = last[0]
-        attempts_per_step = st["attempts"] * world
-        # the collective (N>1) is outside the library's events: use the wall clock of the
-        # barrier-bracketed region as the step time when ranks > 1, device events at N=1
-        step_ms = (wall_ms if world > 1 else dev_ms) / args.steps
+    if ranks.active:
+        agg, last = m["agg"], m["last"]
+        st = last.stats
+        attempts_per_step = st["attempts"]
+        # N = 1: device time of the call (CUDA events on the library's stream); N > 1: wall clock of
+        # the barrier-bracketed region (the devices run concurrently on their own streams)
+        step_ms = (m["wall_ms"] if world > 1 else agg["ms_total"]) / args.steps
         value = attempts_per_step / (step_ms * 1e-3)
         ld = -(-args.n // (1024 if esz == 4 else 512)) * (1024 if esz == 4 else 512)
         row_bytes = ld * esz
-        # dominant kernel: the sweep kernel (init fields + sweeps), one launch per step
-        alg_bytes_per_launch = (agg["row_fetches"] + agg["init_row_fetches"]) * row_bytes / args.steps
-        sweep_s_per_launch = sweep_ms / args.steps * 1e-3
+        # dominant kernel: the sweep kernel (init fields + sweeps), one launch per step and device;
+        # bytes and time per device (the devices run the same kernel side by side)
+        alg_bytes_per_launch = (agg["row_fetches"] + agg["init_row_fetches"]) * row_bytes / args.steps / world
+        sweep_s_per_launch = agg["ms_sweep"] / args.steps * 1e-3   # slowest device
         achieved = alg_bytes_per_launch / sweep_s_per_launch / 1e9
         # best of five: the probe's result moves by +-8% from call to call, the peak is its maximum
-        l2_peak = max(measure_read_bandwidth(64 << 20, 64, device=local_rank) for _ in range(5))
+        l2_peak = max(measure_read_bandwidth(64 << 20, 64, device=0) for _ in range(5))
         peaks, peaks_src = load_measured_peaks()
         q_bytes = args.n * ld * esz
         bound = "l2" if q_bytes <= 100 * (1 << 20) else "hbm"
         peak = l2_peak if bound == "l2" else peaks["hbm_gbs"]
-        # measured once with ncu at the default workload (profiles/r01/ncu_traffic_v54.csv)
-        default_workload = (args.n == 4096 and tries == 131072 and args.sweeps == 32
+        default_workload = (args.n == 4096 and args.tries_per_gpu == 131072 and args.sweeps == 32
                             and args.precision == "f32" and args.beta_min == 1.28
                             and args.beta_max == 19.2)
-        traffic = 136361905408 + 1937762304 if default_workload else None
-        traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum of one launch at this workload "
-                        "(ncu, profiles/r01/ncu_traffic_v54.csv): 0.14 TB of DRAM traffic against "
-                        "14.08 TB of algorithmic row bytes, which are served by the L2 "
-                        "(lts__t_sectors_srcunit_tex_op_read.sum x 32 B = 14.62 TB, hit rate 99.1%)"
-                        if default_workload else "not captured for this workload")
+        traffic, traffic_note = load_traffic(default_workload)
         # exact-energy kernel: 16 DMMA (m8n8k4 = 512 FLOP) per k-step, k up to the diagonal block
         nblk = (args.n + 31) // 32
         dmma_per_tile = 16 * sum((32 * b + 32) // 4 for b in range(nblk))
-        energy_flops = ((tries + 31) // 32) * dmma_per_tile * 512.0
-        energy_tflops = energy_flops / (energy_ms / args.steps * 1e-3) / 1e12
+        energy_flops = ((args.tries_per_gpu + 31) // 32) * dmma_per_tile * 512.0
+        energy_tflops = energy_flops / (agg["ms_energy"] / args.steps * 1e-3) / 1e12
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-        dmma_peak = 128.0 * sm_count(local_rank) * sm_mhz * 1e6 / 1e12
+        dmma_peak = 128.0 * sm_count(0) * sm_mhz * 1e6 / 1e12
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
             "config": config_dict(args, world),
-            "device": device_name(local_rank),
-            "breakdown_ms_per_step": {"sweep_kernel": sweep_ms / args.steps,
-                                      "exact_energy_kernel": energy_ms / args.steps,
-                                      "device_total": dev_ms / args.steps,
-                                      "wall": wall_ms / args.steps},
+            "device": device_name(0),
+            "entry": "osa_multi_anneal (include/onesolver_b200.h): one process, one host thread and "
+                     "stream per GPU, one ncclAllGather of the best records",
+            "nccl": {"comm_nranks_seen": nccl_log_summary(nccl_log), "log": nccl_log or "console"},
+            "breakdown_ms_per_step": {"sweep_kernel": agg["ms_sweep"] / args.steps,
+                                      "exact_energy_kernel": agg["ms_energy"] / args.steps,
+                                      "device_total": agg["ms_total"] / args.steps,
+                                      "wall": m["wall_ms"] / args.steps},
             "accept_frac": agg["accepts"] / max(1, agg["attempts"]),
             "traj_per_row_fetch": st["traj_per_batch"],
-            "sweep_only_attempts_per_s": attempts_per_step / (sweep_ms_max / args.steps * 1e-3),
+            "sweep_only_attempts_per_s": attempts_per_step / (agg["ms_sweep"] / args.steps * 1e-3),
             "roofline": {
-                "bound": bound, "kernel": "k_dense_seq (init fields + sweeps)",
+                "bound": bound, "kernel": "k_dense_seq (init fields + sweeps), per device",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": ("live osa_measure_read_bandwidth over a 64 MiB L2-resident buffer, best of 5"
                                 if bound == "l2" else f"MEASURED_PEAKS.json hbm_gbs ({peaks_src})"),
                 "hbm_peak": peaks["hbm_gbs"], "hbm_peak_source": peaks_src,
                 "frac_of_hbm_peak": achieved / peaks["hbm_gbs"],
                 "algorithmic_bytes_per_launch": alg_bytes_per_launch,
-                "bytes_unshared_per_launch": agg["accepts"] * row_bytes / args.steps,
+                "bytes_unshared_per_launch": agg["accepts"] * row_bytes / args.steps / world,
                 "traffic": traffic, "traffic_unit": "bytes per launch",
                 "traffic_note": traffic_note,
             },
@@ -386,33 +451,54 @@ def run_engine(args):
             },
             "clocks": clocks,
             "gpu_launches": agg["launches"],
-            "best_energy": last[1], "best_index": last[2],
+            "best_energy": last.energy, "best_index": last.index,
         }
-        if e2e_ms is not None:
-            h2d = args.n * args.n * 8 + args.sweeps * 8
-            d2h = tries * 8 + ((args.n + 31) // 32) * 4 + 16 + 64
-            out["e2e"] = {"value": attempts_per_step / (e2e_ms / args.steps * 1e-3), "unit": UNIT,
-                          "ms_per_step": e2e_ms / args.steps,
+        if "e2e_ms" in m:
+            h2d = (args.n * args.n * 8 + args.sweeps * 8) * world
+            d2h = tries * 8 + (((args.n + 31) // 32) * 4 + 16) * world * world + 64
+            out["e2e"] = {"value": attempts_per_step / (m["e2e_ms"] / args.steps * 1e-3), "unit": UNIT,
+                          "ms_per_step": m["e2e_ms"] / args.steps,
                           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                          "what": "osa_problem_create_dense_f64(host Q) + osa_anneal(host outputs) "
-                                  "+ osa_problem_destroy per step, wall clock"}
+                          "what": "osa_multi_create_dense_f64(pinned host Q) + osa_multi_anneal(host "
+                                  "outputs) + osa_multi_destroy per step, wall clock"}
+            if pageable is not None:
+                out["e2e"]["pageable_input"] = {
+                    "value": attempts_per_step / (pageable / pageable_steps * 1e-3),
+                    "ms_per_step": pageable / pageable_steps, "steps": pageable_steps,
+                    "what": "the same with Q in ordinary (pageable) host memory, as a caller of "
+                            "sa::anneal has it"}
+        if others:
+            out["other_configs"] = [o for o in others if o]
         if not args.no_cpu_baseline and world == 1:
             base, _, _ = cpu_reference_sample(args, q)
             out["cpu_baseline"] = base
         print(json.dumps(out), flush=True)
+    ranks.close()
 
-    prob.close()
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+
+def load_traffic(default_workload):
+    """DRAM traffic of one sweep launch at the default workload, from the committed ncu capture."""
+    if not default_workload:
+        return None, "not captured for this workload"
+    path = os.path.join(ROOT, "profiles", "r02", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        return t["dram_bytes"], t["note"]
+    except Exception:
+        return 136361905408 + 1937762304, (
+            "dram__bytes_read.sum + dram__bytes_write.sum of one launch at this workload (ncu, "
+            "profiles/r01/ncu_traffic_v54.csv): 0.14 TB of DRAM traffic against 14.08 TB of "
+            "algorithmic row bytes, which are served by the L2")
 
 
 # --------------------------------------------------------------------------- configs 3 and 4
 def other_config_spec(args):
     """BASELINE.json configs 3 (dense fp64 N=1024, 16384 tries, 1000 sweeps) and 4 (sparse
-    Pegasus-like N=5627 CSR, 65536 tries, linear schedule): instance, schedule, problem factory.
-    Weak scaling: every GPU anneals the config's full number of tries (global ids rank*tries...)."""
-    from onesolver_b200 import (Problem, capi, construct_geometric_beta_schedule,
+    Pegasus-like N=5627 CSR, 65536 tries, linear schedule), and the reference's own random-site loop
+    on the headline instance: instance, schedule, problem factory.
+    Weak scaling: every GPU anneals the config's full number of tries."""
+    from onesolver_b200 import (MultiProblem, capi, construct_geometric_beta_schedule,
                                 construct_linear_beta_schedule)
     from onesolver_b200 import problems as gen
     if args.workload == "config3":
@@ -421,10 +507,24 @@ def other_config_spec(args):
         sched = construct_geometric_beta_schedule(0.02 * 32, 0.30 * 32, sweeps)
         return {"metric": "spin-flip attempts/s, dense fp64 N=1024", "n": n, "tries": tries,
                 "sweeps": sweeps, "sched": sched, "dtype": "f64", "esz": 8,
-                "make": lambda dev, src=q: Problem.dense(src, device=dev, sweep_precision=capi.SWEEP_F64),
+                "mode": capi.MODE_SEQUENTIAL_SWEEP,
+                "make": lambda devs, src=q: MultiProblem.dense(src, devices=devs, sweep_precision=capi.SWEEP_F64),
                 "host_input": q, "h2d": q.nbytes + sched.nbytes,
                 "workload": f"BASELINE config 3: dense fp64 N={n} U(-1,1) QUBO, {tries} tries/GPU, "
                             f"{sweeps} sequential sweeps, reference accept rule, geometric beta 0.64->9.6"}
+    if args.workload == "random_site":
+        # the reference's loop (annealing.hpp:97-101): one attempt per iteration at a random site
+        n, tries, iters = 4096, 16384, 4096
+        q = gen.dense_uniform_qubo(n, seed=2024 + 5)
+        sched = construct_geometric_beta_schedule(1.28, 19.2, iters)
+        return {"metric": "spin-flip attempts/s, dense N=4096, random-site (reference loop)", "n": n,
+                "tries": tries, "sweeps": iters, "sched": sched, "dtype": "f32", "esz": 4,
+                "mode": capi.MODE_RANDOM_SITE,
+                "make": lambda devs, src=q: MultiProblem.dense(src, devices=devs, sweep_precision=capi.SWEEP_F32),
+                "host_input": q, "h2d": q.nbytes + sched.nbytes,
+                "workload": f"reference loop on the headline instance: dense N={n}, {tries} tries/GPU, "
+                            f"{iters} single-flip attempts per trajectory at random sites (annealing.hpp:"
+                            f"97-101), reference accept rule, geometric beta 1.28->19.2, fp32 fields"}
     n, tries, sweeps = 5627, 65536, 100
     rowptr, col, val, diag = gen.sparse_random_graph(n, 15, seed=2024 + 4)
     sched = construct_linear_beta_schedule(0.5, 5.0, sweeps)
@@ -432,7 +532,8 @@ def other_config_spec(args):
     return {"metric": "spin-flip attempts/s, sparse N=5627 (CSR)", "n": n, "tries": tries,
             "sweeps": sweeps, "sched": sched, "dtype": args.precision,
             "esz": 4 if args.precision == "f32" else 8, "nnz": int(len(col)),
-            "make": lambda dev: Problem.csr(rowptr, col, val, diag, device=dev, sweep_precision=prec),
+            "mode": capi.MODE_SEQUENTIAL_SWEEP,
+            "make": lambda devs: MultiProblem.csr(rowptr, col, val, diag, devices=devs, sweep_precision=prec),
             "host_input": None,
             "h2d": rowptr.nbytes + col.nbytes + val.nbytes + diag.nbytes + sched.nbytes,
             "workload": f"BASELINE config 4: sparse Pegasus-like N={n} CSR ({len(col) // 2} couplers, "
@@ -440,12 +541,72 @@ def other_config_spec(args):
                         f"accept rule, linear beta 0.5->5.0, fields in {args.precision}"}
 
 
+def sub_record(spec, m, world, steps, warmup, l2_peak, clocks):
+    """One record of the bench line for a workload other than the headline one."""
+    agg, st = m["agg"], m["last"].stats
+    attempts_per_step = st["attempts"]
+    step_ms = (m["wall_ms"] if world > 1 else agg["ms_total"]) / steps
+    sweep_s = agg["ms_sweep"] / steps * 1e-3
+    if "nnz" in spec:
+        # every warp (32 trajectories) streams the CSR once per sweep: nnz x (index + value)
+        alg = -(-spec["tries"] // 32) * spec["sweeps"] * spec["nnz"] * (4 + spec["esz"])
+        what = "CSR blocks streamed per device: warps x sweeps x nnz x (4 B index + value)"
+    else:
+        unit = 1024 if spec["esz"] == 4 else 512
+        ld = -(-spec["n"] // unit) * unit
+        alg = (agg["row_fetches"] + agg["init_row_fetches"]) * ld * spec["esz"] / steps / world
+        what = "Q rows streamed per device: (row_fetches + init_row_fetches) x ld x element size"
+    rec = {"metric": spec["metric"], "value": attempts_per_step / (step_ms * 1e-3), "unit": UNIT,
+           "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": step_ms,
+           "scaling": "weak", "dtype": spec["dtype"],
+           "config": {"workload": spec["workload"], "n": spec["n"], "tries_per_gpu": spec["tries"],
+                      "sweeps": spec["sweeps"], "accept_rule": "reference", "seed": 1234},
+           "breakdown_ms_per_step": {"sweep_kernel": agg["ms_sweep"] / steps,
+                                     "exact_energy_kernel": agg["ms_energy"] / steps,
+                                     "device_total": agg["ms_total"] / steps, "wall": m["wall_ms"] / steps},
+           "accept_frac": agg["accepts"] / max(1, agg["attempts"]),
+           "kernel": st["kernel_id"], "traj_per_row_fetch": st["traj_per_batch"],
+           "roofline": {"bound": "l2", "kernel": "sweep kernel, per device",
+                        "achieved": alg / sweep_s / 1e9, "peak": l2_peak, "unit": "GB/s",
+                        "frac": alg / sweep_s / 1e9 / l2_peak,
+                        "algorithmic_bytes_per_launch": alg, "algorithmic_bytes": what, "traffic": None},
+           "clocks": clocks, "gpu_launches": agg["launches"],
+           "best_energy": m["last"].energy, "best_index": m["last"].index}
+    if "e2e_ms" in m:
+        rec["e2e"] = {"value": attempts_per_step / (m["e2e_ms"] / steps * 1e-3), "unit": UNIT,
+                      "ms_per_step": m["e2e_ms"] / steps, "h2d_bytes_per_step": int(spec["h2d"]) * world,
+                      "d2h_bytes_per_step": spec["tries"] * world * 8 + ((spec["n"] + 31) // 32) * 4 + 16 + 64,
+                      "what": "osa_multi_create_*(host arrays) + osa_multi_anneal(host outputs) + "
+                              "osa_multi_destroy per step, wall clock"}
+    return rec
+
+
+def run_sub_record(ranks, args, name, devices):
+    """A reduced-step measurement of another workload inside the headline run (W = 1, K = 1)."""
+    import copy
+    a = copy.copy(args)
+    a.workload = name
+    world = len(devices)
+    spec = other_config_spec(a) if ranks.active else None
+    sampler = ClockSampler(devices)
+    if ranks.active:
+        sampler.start()
+        make = lambda: spec["make"](devices)  # noqa: E731
+        m = measure(ranks, make, spec["sched"], spec["sweeps"], spec["tries"] * world, 1, 1,
+                    spec["mode"], None if args.no_e2e else make)
+        clocks = sampler.stop()
+        from onesolver_b200 import measure_read_bandwidth
+        l2_peak = max(measure_read_bandwidth(64 << 20, 64, device=0) for _ in range(3))
+        return sub_record(spec, m, world, 1, 1, l2_peak, clocks)
+    measure(ranks, None, None, 0, 0, 1, 1, 0, None if args.no_e2e else (lambda: None))
+    return None
+
+
 def run_other_config(args):
+    """`--workload config3|config4|random_site`: that workload alone, with the full K / W."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        if rank == 0:
+        if int(os.environ.get("RANK", "0")) == 0:
             print(json.dumps({"impl": "reference", "unavailable":
                               "the reference arm is defined for the headline workload (config5) only"}))
         return
@@ -454,128 +615,26 @@ def run_other_config(args):
                f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port",
                "29533", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
-    from onesolver_b200 import capi, device_name, measure_read_bandwidth
-
-    dist = torch = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    spec = other_config_spec(args)
-    tries, sweeps, sched = spec["tries"], spec["sweeps"], spec["sched"]
-    first_try = rank * tries
-    mode = capi.MODE_SEQUENTIAL_SWEEP
-    prob = spec["make"](local_rank)
-
-    def reduce_best(res):
-        if dist is None:
-            return res.energy, res.index
-        from onesolver_b200.multi import gather_best
-        e, idx, _ = gather_best(dist, torch, res.energy, res.index, res.state,
-                                torch.device("cuda", local_rank))
-        return e, idx
-
-    def step(p=prob, **kw):
-        res = p.anneal(sched, sweeps, tries, first_try=first_try, mode=mode, **kw)
-        return res.stats, reduce_best(res)
-
-    for _ in range(args.warmup):
-        step()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    nccl_log_setup()
+    ranks = Ranks()
+    from onesolver_b200 import measure_read_bandwidth
+    devices = list(range(world))
+    spec = other_config_spec(args) if ranks.active else None
+    sampler = ClockSampler(devices)
+    if ranks.active:
         sampler.start()
-    barrier()
-    t0 = time.perf_counter()
-    tot = {"ms_total": 0.0, "ms_sweep": 0.0, "ms_energy": 0.0, "attempts": 0, "accepts": 0,
-           "row_fetches": 0, "init_row_fetches": 0, "launches": 0}
-    for _ in range(args.steps):
-        st, best = step()
-        for k in tot:
-            tot[k] += st[k]
-    barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    clocks = sampler.stop() if rank == 0 else None
-
-    e2e_ms = None
-    if not args.no_e2e:
-        def e2e_step():
-            with spec["make"](local_rank) as p2:  # host arrays -> device layouts, every step
-                step(p2, want_energies=True)
-        e2e_step()
-        barrier()
-        t1 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
-        barrier()
-        e2e_ms = (time.perf_counter() - t1) * 1e3
-
-    def rank_max(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    dev_ms, wall_ms = rank_max(tot["ms_total"]), rank_max(wall_ms)
-    if e2e_ms is not None:
-        e2e_ms = rank_max(e2e_ms)
-    if rank == 0:
-        attempts_per_step = st["attempts"] * world
-        step_ms = (wall_ms if world > 1 else dev_ms) / args.steps
-        sweep_s = tot["ms_sweep"] / args.steps * 1e-3
-        if args.workload == "config3":
-            ld = -(-spec["n"] // 512) * 512
-            alg = (tot["row_fetches"] + tot["init_row_fetches"]) * ld * 8 / args.steps
-            what = "Q rows streamed: (row_fetches + init_row_fetches) x ld x 8 B"
-        else:
-            # every warp (32 trajectories) streams the CSR once per sweep: nnz x (index + value)
-            alg = -(-tries // 32) * sweeps * spec["nnz"] * (4 + spec["esz"])
-            what = "CSR blocks streamed: warps x sweeps x nnz x (4 B index + value)"
-        l2_peak = max(measure_read_bandwidth(64 << 20, 64, device=local_rank) for _ in range(5))
-        out = {"metric": spec["metric"], "value": attempts_per_step / (step_ms * 1e-3), "unit": UNIT,
-               "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
-               "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-               "dtype": spec["dtype"], "data": "synthetic",
-               "config": {"workload": spec["workload"], "n": spec["n"], "tries_per_gpu": tries,
-                          "sweeps": sweeps, "mode": "sequential_sweep", "accept_rule": "reference",
-                          "seed": 1234, "parallelism": f"trajectory shards x{world}, problem replicated",
-                          "l2_hygiene": "the problem is L2-resident by design; every step writes and "
-                                        "re-reads the per-trajectory state arrays"},
-               "device": device_name(local_rank),
-               "breakdown_ms_per_step": {"sweep_kernel": tot["ms_sweep"] / args.steps,
-                                         "exact_energy_kernel": tot["ms_energy"] / args.steps,
-                                         "device_total": dev_ms / args.steps,
-                                         "wall": wall_ms / args.steps},
-               "accept_frac": tot["accepts"] / max(1, tot["attempts"]),
-               "kernel_id": st["kernel_id"], "traj_per_row_fetch": st["traj_per_batch"],
-               "roofline": {"bound": "l2", "kernel": "sweep kernel", "achieved": alg / sweep_s / 1e9,
-                            "peak": l2_peak, "unit": "GB/s", "frac": alg / sweep_s / 1e9 / l2_peak,
-                            "peak_source": "live osa_measure_read_bandwidth over a 64 MiB L2-resident "
-                                           "buffer, best of 5",
-                            "algorithmic_bytes_per_launch": alg, "algorithmic_bytes": what,
-                            "traffic": None,
-                            "note": "issue-/latency-bound kernel at this shape (DESIGN.md section 3); "
-                                    "the bandwidth fraction is reported, not targeted"},
-               "clocks": clocks, "gpu_launches": tot["launches"],
-               "best_energy": best[0], "best_index": best[1]}
-        if e2e_ms is not None:
-            out["e2e"] = {"value": attempts_per_step / (e2e_ms / args.steps * 1e-3), "unit": UNIT,
-                          "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(spec["h2d"]),
-                          "d2h_bytes_per_step": tries * 8 + ((spec["n"] + 31) // 32) * 4 + 16 + 64,
-                          "what": "osa_problem_create_*(host arrays) + osa_anneal(host outputs) + "
-                                  "osa_problem_destroy per step, wall clock"}
-        print(json.dumps(out), flush=True)
-    prob.close()
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+        make = lambda: spec["make"](devices)  # noqa: E731
+        m = measure(ranks, make, spec["sched"], spec["sweeps"], spec["tries"] * world, args.steps,
+                    args.warmup, spec["mode"], None if args.no_e2e else make)
+        clocks = sampler.stop()
+        l2_peak = max(measure_read_bandwidth(64 << 20, 64, device=0) for _ in range(5))
+        rec = sub_record(spec, m, world, args.steps, args.warmup, l2_peak, clocks)
+        rec.update({"higher_is_better": True, "vs_baseline": None, "data": "synthetic"})
+        print(json.dumps(rec), flush=True)
+    else:
+        measure(ranks, None, None, 0, 0, args.steps, args.warmup, 0,
+                None if args.no_e2e else (lambda: None))
+    ranks.close()
 
 
 def main():

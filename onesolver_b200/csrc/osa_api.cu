@@ -102,6 +102,15 @@ void dev_free(P *ptr, cudaStream_t stream) {
   if (ptr) cudaFreeAsync(const_cast<void *>(static_cast<const void *>(ptr)), stream);
 }
 
+}  // namespace
+
+cudaError_t osa_pool_alloc(void **ptr, size_t bytes, cudaStream_t stream) {
+  return dev_alloc(reinterpret_cast<char **>(ptr), bytes, stream);
+}
+void osa_pool_free(void *ptr, cudaStream_t stream) { dev_free(static_cast<char *>(ptr), stream); }
+
+namespace {
+
 // build the sweep-precision layouts from a dense upload
 template <typename TIn, typename T>
 __global__ void k_prep_dense(const TIn *__restrict__ in, int n, T *__restrict__ qoff, size_t ld,

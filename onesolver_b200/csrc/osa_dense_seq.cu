@@ -306,18 +306,21 @@ static bool use_ws() {
   const char *e = getenv("OSA_DS_WS");
   return !(e && e[0] == '0');
 }
-// ... and of those, the free-running variant (osa_dense_seq_ws2.cu) unless OSA_WS_FLOW=0 asks for the
-// lock-step one (A/B runs; both give the same results bit for bit).
-#ifndef OSA_WS_FLOW_DEFAULT
-#define OSA_WS_FLOW_DEFAULT 0
-#endif
-static bool use_flow() {
+// ... and of those, the free-running variant (osa_dense_seq_ws2.cu) where it is the faster one:
+// its flip-to-flip decide walk wins in the cold sweeps of a schedule and loses when most sites
+// flip, and a decide warp walks R/4 trajectories side by side.  Measured on the bench schedule
+// (profiles/r02/flow_check4_parity_and_probes.txt): N = 4096 fp32 (R = 12) 0.453 against 0.444 of
+// the L2 roofline, the R = 16 shapes (N <= 2048) 10-25 % slower.  OSA_WS_FLOW=0/1 forces one of
+// the two for A/B runs; both give the same results bit for bit.
+static bool use_flow(size_t ld, int elem_bytes) {
   const char *e = getenv("OSA_WS_FLOW");
-  return e ? e[0] != '0' : OSA_WS_FLOW_DEFAULT != 0;
+  if (e) return e[0] != '0';
+  return elem_bytes == 4 && ld == 4096;
 }
 template <typename T>
 static cudaError_t launch_ws_any(const DenseParams<T> &p, cudaStream_t s, LaunchInfo *info) {
-  return use_flow() ? launch_dense_seq_flow<T>(p, s, info) : launch_dense_seq_ws<T>(p, s, info);
+  return use_flow(p.ld, (int)sizeof(T)) ? launch_dense_seq_flow<T>(p, s, info)
+                                        : launch_dense_seq_ws<T>(p, s, info);
 }
 
 template <>

@@ -52,6 +52,10 @@ int osa_fail(int code, const char *fmt, ...);
 // problem's device and stream -- the record that osa_multi_anneal gathers over NCCL.
 cudaError_t osa_pack_best(osa_problem *p, uint64_t first_try, unsigned char *d_rec);
 
+// stream-ordered allocations from the library's private pool of the current device (osa_api.cu)
+cudaError_t osa_pool_alloc(void **ptr, size_t bytes, cudaStream_t stream);
+void osa_pool_free(void *ptr, cudaStream_t stream);
+
 namespace osa {
 // Every API call runs on the device of its problem and leaves the caller's current device as it
 // found it (a host application with several GPUs keeps its own cudaSetDevice state).

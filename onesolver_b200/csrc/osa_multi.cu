@@ -13,6 +13,9 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <new>
 #include <string>
 #include <thread>
@@ -22,10 +25,18 @@
 
 using namespace osa;
 
+// The communicators of a device list are created once per process and shared by every osa_multi
+// with that list (ncclCommInitAll costs hundreds of milliseconds; sa::anneal creates and destroys
+// a problem per call).  Calls on handles that share communicators are serialised by `busy`.
+struct CommSet {
+  std::vector<ncclComm_t> comms;
+  std::mutex busy;
+};
+
 struct osa_multi {
   std::vector<int> devices;
   std::vector<osa_problem *> problems;
-  std::vector<ncclComm_t> comms;
+  std::shared_ptr<CommSet> comm_set;
   std::vector<unsigned char *> d_rec;  // per device: this device's record
   std::vector<unsigned char *> d_all;  // per device: the gathered records of all devices
   int n = 0, nw = 0;
@@ -163,18 +174,28 @@ int multi_create(const int *devices, int num_devices, int n, Create create, osa_
     if (!nccl.error.empty()) {
       rc = osa_fail(OSA_ERR_UNSUPPORTED, "NCCL is not available: %s", nccl.error.c_str());
     } else {
-      m->comms.assign(g, nullptr);
-      ncclResult_t nr = nccl.comm_init_all(m->comms.data(), g, m->devices.data());
-      if (nr != ncclSuccess) {
-        m->comms.clear();
-        rc = osa_fail(OSA_ERR_CUDA, "ncclCommInitAll over %d devices failed: %s", g, nccl.error_string(nr));
+      static std::mutex cache_mutex;
+      static std::map<std::vector<int>, std::shared_ptr<CommSet>> cache;  // lives as long as the process
+      std::lock_guard<std::mutex> lock(cache_mutex);
+      auto it = cache.find(m->devices);
+      if (it != cache.end()) {
+        m->comm_set = it->second;
+      } else {
+        auto set = std::make_shared<CommSet>();
+        set->comms.assign(g, nullptr);
+        ncclResult_t nr = nccl.comm_init_all(set->comms.data(), g, m->devices.data());
+        if (nr != ncclSuccess)
+          rc = osa_fail(OSA_ERR_CUDA, "ncclCommInitAll over %d devices failed: %s", g, nccl.error_string(nr));
+        else
+          cache[m->devices] = m->comm_set = set;
       }
     }
   }
   for (int k = 0; k < g && rc == OSA_OK; ++k) {
     cudaError_t e = cudaSetDevice(m->devices[k]);
-    if (e == cudaSuccess) e = cudaMalloc(&m->d_rec[k], m->rec_bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&m->d_all[k], m->rec_bytes * g);
+    cudaStream_t st = m->problems[k]->stream;
+    if (e == cudaSuccess) e = osa_pool_alloc(reinterpret_cast<void **>(&m->d_rec[k]), m->rec_bytes, st);
+    if (e == cudaSuccess) e = osa_pool_alloc(reinterpret_cast<void **>(&m->d_all[k]), m->rec_bytes * g, st);
     if (e != cudaSuccess) rc = osa_fail(OSA_ERR_CUDA, "gather buffers on device %d: %s", m->devices[k], cudaGetErrorString(e));
   }
   if (rc) {
@@ -222,11 +243,10 @@ int osa_multi_destroy(osa_multi *m) {
   DeviceGuard guard;
   for (size_t k = 0; k < m->devices.size(); ++k) {
     cudaSetDevice(m->devices[k]);
-    if (k < m->d_rec.size() && m->d_rec[k]) cudaFree(m->d_rec[k]);
-    if (k < m->d_all.size() && m->d_all[k]) cudaFree(m->d_all[k]);
+    cudaStream_t st = (k < m->problems.size() && m->problems[k]) ? m->problems[k]->stream : nullptr;
+    if (k < m->d_rec.size() && m->d_rec[k]) osa_pool_free(m->d_rec[k], st);
+    if (k < m->d_all.size() && m->d_all[k]) osa_pool_free(m->d_all[k], st);
   }
-  for (auto c : m->comms)
-    if (c) nccl_api().comm_destroy(c);
   for (auto p : m->problems) osa_problem_destroy(p);
   delete m;
   return OSA_OK;
@@ -258,6 +278,8 @@ int osa_multi_anneal(osa_multi *m, const double *beta_schedule, const osa_anneal
   std::vector<std::vector<unsigned char>> host_all(g);
   memset(st.data(), 0, sizeof(osa_stats) * g);
   DeviceGuard guard;
+  std::unique_lock<std::mutex> comm_lock;
+  if (m->comm_set) comm_lock = std::unique_lock<std::mutex>(m->comm_set->busy);
   int rc = for_each_device(g, [&](int k) -> int {
     osa_problem *p = m->problems[k];
     uint64_t first = 0, count = 0;
@@ -281,7 +303,7 @@ int osa_multi_anneal(osa_multi *m, const double *beta_schedule, const osa_anneal
     // the one collective of the call: every device's {energy, id, state}
     if (g > 1) {
       const NcclApi &nccl = nccl_api();
-      ncclResult_t nr = nccl.all_gather(m->d_rec[k], m->d_all[k], m->rec_bytes, ncclUint8, m->comms[k], p->stream);
+      ncclResult_t nr = nccl.all_gather(m->d_rec[k], m->d_all[k], m->rec_bytes, ncclUint8, m->comm_set->comms[k], p->stream);
       if (nr != ncclSuccess) return osa_fail(OSA_ERR_CUDA, "ncclAllGather: %s", nccl.error_string(nr));
     } else {
       e = cudaMemcpyAsync(m->d_all[k], m->d_rec[k], m->rec_bytes, cudaMemcpyDeviceToDevice, p->stream);
