@@ -126,6 +126,19 @@ int osa_anneal(osa_problem *p, const double *beta_schedule, const osa_anneal_par
                double *best_energies, uint32_t *best_states_packed, uint8_t *best_state,
                double *best_energy, uint64_t *best_index, osa_stats *stats);
 
+/* osa_anneal plus the FLIP TRACE of every trajectory: trace_hash[num_tries] (may be NULL) receives a
+ * 64-bit FNV-1a hash over the accepted flips in the order they happen, one update per (step, block
+ * of 32 sites) with at least one accepted flip:
+ *     h = 0xcbf29ce484222325;  h = (h ^ step) * 0x100000001b3;  h = (h ^ (block << 32 | mask)) * 0x100000001b3
+ * step = counter of the random stream (sequential mode: sweep number, random-site mode: attempt
+ * number), mask = the accepted sites of the block.  It pins the whole spin sequence of a
+ * trajectory, not only its best state; the host replay computes the same value
+ * (oracle/osa_oracle.c), which is how BASELINE.json's "replayed trajectories" criterion is tested. */
+int osa_anneal_traced(osa_problem *p, const double *beta_schedule, const osa_anneal_params *params,
+                      double *best_energies, uint32_t *best_states_packed, uint8_t *best_state,
+                      double *best_energy, uint64_t *best_index, uint64_t *trace_hash,
+                      osa_stats *stats);
+
 /* ---- parallel tempering on top of the same sweep kernel.  The reference has no such sampler; its
  *      benchmark report recommends one (benchmarks/annealing/performance.md:54-59).
  * num_groups independent runs of num_replicas replicas each; betas[num_replicas] is the ladder

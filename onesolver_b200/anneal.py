@@ -30,13 +30,15 @@ def construct_geometric_beta_schedule(beta_min, beta_max, num_iter):
 
 
 class AnnealResult:
-    def __init__(self, state, energy, index, stats, best_energies=None, best_states_packed=None):
+    def __init__(self, state, energy, index, stats, best_energies=None, best_states_packed=None,
+                 trace_hash=None):
         self.state = state            # uint8[N] (qubo::Solution::state)
         self.energy = energy          # float   (qubo::Solution::energy)
         self.index = index            # global id of the winning trajectory
         self.stats = stats            # dict of osa_stats
         self.best_energies = best_energies
         self.best_states_packed = best_states_packed
+        self.trace_hash = trace_hash  # uint64[num_tries]: flip trace per trajectory (want_trace)
 
 
 class Problem:
@@ -97,7 +99,8 @@ class Problem:
 
     def anneal(self, beta_schedule, num_iter, num_tries, sweeps_per_beta=1, seed=1234,
                first_try=0, mode=capi.MODE_RANDOM_SITE, accept_rule=capi.ACCEPT_REFERENCE,
-               kernel_variant=capi.KID_AUTO, want_energies=False, want_states=False):
+               kernel_variant=capi.KID_AUTO, want_energies=False, want_states=False,
+               want_trace=False):
         """sa::anneal(instance, q, beta_schedule, num_iter, num_tries, sweeps_per_beta)."""
         lib = capi.load()
         sched = np.ascontiguousarray(beta_schedule, dtype=np.float64)
@@ -108,16 +111,18 @@ class Problem:
                                 accept_rule=accept_rule, kernel_variant=kernel_variant, flags=0)
         energies = np.empty(num_tries, dtype=np.float64) if want_energies else None
         states = np.empty((num_tries, self.nw), dtype=np.uint32) if want_states else None
+        trace = np.empty(num_tries, dtype=np.uint64) if want_trace else None
         state = np.empty(self.n, dtype=np.uint8)
         e = ctypes.c_double()
         idx = ctypes.c_uint64()
         st = capi.Stats()
-        capi.check(lib.osa_anneal(self._h, sched.ctypes.data, ctypes.byref(prm),
-                                  energies.ctypes.data if want_energies else None,
-                                  states.ctypes.data if want_states else None,
-                                  state.ctypes.data, ctypes.byref(e), ctypes.byref(idx),
-                                  ctypes.byref(st)))
-        return AnnealResult(state, e.value, idx.value, st.as_dict(), energies, states)
+        capi.check(lib.osa_anneal_traced(self._h, sched.ctypes.data, ctypes.byref(prm),
+                                         energies.ctypes.data if want_energies else None,
+                                         states.ctypes.data if want_states else None,
+                                         state.ctypes.data, ctypes.byref(e), ctypes.byref(idx),
+                                         trace.ctypes.data if want_trace else None,
+                                         ctypes.byref(st)))
+        return AnnealResult(state, e.value, idx.value, st.as_dict(), energies, states, trace)
 
     def parallel_tempering(self, betas, num_groups, num_rounds, sweeps_per_round, seed=1234,
                            first_group=0, accept_rule=capi.ACCEPT_BOLTZMANN, want_energies=False,

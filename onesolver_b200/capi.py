@@ -22,6 +22,7 @@ EXPORTED_SYMBOLS = [
     "osa_abi_version", "osa_last_error", "osa_device_count", "osa_device_name",
     "osa_kernel_name", "osa_problem_create_dense_f64", "osa_problem_create_dense_f32",
     "osa_problem_create_csr_f64", "osa_problem_destroy", "osa_problem_size", "osa_anneal",
+    "osa_anneal_traced",
     "osa_pt_anneal", "osa_energy_batch", "osa_exhaustive_dense_f64", "osa_host_alloc_pinned",
     "osa_host_free_pinned", "osa_measure_read_bandwidth",
     "osa_multi_create_dense_f64", "osa_multi_create_dense_f32", "osa_multi_create_csr_f64",
@@ -117,6 +118,8 @@ def load():
     lib.osa_problem_size.argtypes = [vp, P(i32), P(i32), P(i32)]
     lib.osa_anneal.argtypes = [vp, vp, P(AnnealParams), vp, vp, vp, P(ctypes.c_double), P(u64),
                                P(Stats)]
+    lib.osa_anneal_traced.argtypes = [vp, vp, P(AnnealParams), vp, vp, vp, P(ctypes.c_double), P(u64),
+                                      vp, P(Stats)]
     lib.osa_pt_anneal.argtypes = [vp, vp, P(PtParams), vp, vp, vp, P(ctypes.c_double), P(u64),
                                   P(Stats)]
     lib.osa_energy_batch.argtypes = [vp, vp, u64, vp]

@@ -413,7 +413,24 @@ int osa_problem_create_csr_f64(const int32_t *rowptr, const int32_t *col, const 
   step(dev_alloc(&p->d_val64, nnz_a * sizeof(double), p->stream));
   step(dev_alloc(&p->d_diag64, (size_t)n * sizeof(double), p->stream));
   step(dev_alloc(&p->d_val, (nnz_a + (size_t)n) * esz, p->stream));
+  // groups of four consecutive sites (32b + 4g ..) without a coupling among them: the sparse sweep
+  // gathers their fields side by side (k_sparse)
+  const int nblk32 = (n + 31) / 32;
+  std::vector<uint32_t> indep((size_t)nblk32, 0u);
+  for (int i0 = 0; i0 + 4 <= n; i0 += 4) {
+    bool free = true;
+    for (int a = i0; a < i0 + 4 && free; ++a)
+      for (int32_t q = rowptr[a]; q < rowptr[a + 1]; ++q)
+        if (col[q] >= i0 && col[q] < i0 + 4) {
+          free = false;
+          break;
+        }
+    if (free) indep[(size_t)(i0 >> 5)] |= 1u << ((i0 & 31) >> 2);
+  }
+  step(dev_alloc(&p->d_indep, (size_t)nblk32 * sizeof(uint32_t), p->stream));
   if (e == cudaSuccess) {
+    step(cudaMemcpyAsync(p->d_indep, indep.data(), (size_t)nblk32 * sizeof(uint32_t),
+                         cudaMemcpyHostToDevice, p->stream));
     step(cudaMemcpyAsync(p->d_rowptr, rowptr, (size_t)(n + 1) * sizeof(int32_t),
                          cudaMemcpyHostToDevice, p->stream));
     if (nnz > 0) {
@@ -457,6 +474,7 @@ int osa_problem_destroy(osa_problem *p) {
     dev_free(p->d_val, st);
     dev_free(p->d_val64, st);
     dev_free(p->d_diag64, st);
+    dev_free(p->d_indep, st);
   } else {
     dev_free(p->d_qoff, st);
     dev_free(p->d_diag, st);
@@ -466,6 +484,7 @@ int osa_problem_destroy(osa_problem *p) {
   dev_free(p->d_energy, st);
   dev_free(p->d_states, st);
   dev_free(p->d_xbest_ws, st);
+  dev_free(p->d_trace, st);
   dev_free(p->d_tscale, st);
   dev_free(p->d_counters, st);
   dev_free(p->d_arg_idx, st);
@@ -489,6 +508,14 @@ int osa_problem_size(const osa_problem *p, int *n, int *is_sparse, int *sweep_pr
 int osa_anneal(osa_problem *p, const double *beta_schedule, const osa_anneal_params *prm,
                double *best_energies, uint32_t *best_states_packed, uint8_t *best_state,
                double *best_energy, uint64_t *best_index, osa_stats *stats) {
+  return osa_anneal_traced(p, beta_schedule, prm, best_energies, best_states_packed, best_state,
+                           best_energy, best_index, nullptr, stats);
+}
+
+int osa_anneal_traced(osa_problem *p, const double *beta_schedule, const osa_anneal_params *prm,
+                      double *best_energies, uint32_t *best_states_packed, uint8_t *best_state,
+                      double *best_energy, uint64_t *best_index, uint64_t *trace_hash,
+                      osa_stats *stats) {
   if (!p || !beta_schedule || !prm) return fail(OSA_ERR_INVALID, "null argument");
   if (prm->num_iter < 1) return fail(OSA_ERR_INVALID, "num_iter must be >= 1");
   if (prm->sweeps_per_beta < 1) return fail(OSA_ERR_INVALID, "sweeps_per_beta must be >= 1");
@@ -513,6 +540,13 @@ int osa_anneal(osa_problem *p, const double *beta_schedule, const osa_anneal_par
   if (rc) return rc;
   rc = ensure_workspace(p, prm->num_tries, prm->num_iter);
   if (rc) return rc;
+  if (trace_hash && prm->num_tries > p->cap_trace) {
+    dev_free(p->d_trace, p->stream);
+    p->d_trace = nullptr;
+    p->cap_trace = 0;
+    CUDA_TRY(dev_alloc(&p->d_trace, prm->num_tries * sizeof(unsigned long long), p->stream));
+    p->cap_trace = prm->num_tries;
+  }
 
   // threshold scale per iteration: accept iff dE < tscale * (-ln u)
   const bool f32 = p->prec == OSA_SWEEP_F32;
@@ -577,6 +611,8 @@ int osa_anneal(osa_problem *p, const double *beta_schedule, const osa_anneal_par
       sp.log_base = 0;
       sp.nw = p->nw;
       sp.counters = p->d_counters;
+      sp.trace_hash = trace_hash ? p->d_trace : nullptr;
+      sp.indep = p->d_indep;
       return launch_sparse<T>(sp, p->stream, &info);
     };
     CUDA_TRY(f32 ? run(float()) : run(double()));
@@ -599,6 +635,7 @@ int osa_anneal(osa_problem *p, const double *beta_schedule, const osa_anneal_par
       dp.best_states = p->d_states;
       dp.nw = p->nw;
       dp.counters = p->d_counters;
+      dp.trace_hash = trace_hash ? p->d_trace : nullptr;
       return kid == KID_DENSE_SEQ ? launch_dense_seq<T>(dp, p->stream, &info)
                                   : launch_dense_generic<T>(dp, p->stream, &info);
     };
@@ -633,6 +670,9 @@ int osa_anneal(osa_problem *p, const double *beta_schedule, const osa_anneal_par
   if (best_states_packed)
     CUDA_TRY(cudaMemcpyAsync(best_states_packed, p->d_states,
                              (size_t)prm->num_tries * p->nw * sizeof(uint32_t),
+                             cudaMemcpyDeviceToHost, p->stream));
+  if (trace_hash)
+    CUDA_TRY(cudaMemcpyAsync(trace_hash, p->d_trace, prm->num_tries * sizeof(uint64_t),
                              cudaMemcpyDeviceToHost, p->stream));
   std::vector<uint32_t> win(p->nw);
   CUDA_TRY(cudaMemcpyAsync(win.data(), p->d_states + (size_t)h_idx * p->nw,

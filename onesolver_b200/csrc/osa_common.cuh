@@ -111,6 +111,20 @@ template <> struct Vec16<double> {
   static constexpr int V = 2;
 };
 
+// Flip trace of a trajectory (osa_anneal_traced): 64-bit FNV-1a over the accepted flips, one update
+// per (step, block of 32 sites) with at least one accepted flip, in the order they happen:
+//   h = (h ^ step) * P;  h = (h ^ ((block << 32) | mask)) * P
+// step = the counter of the random stream (sequential mode: the sweep number; random-site mode: the
+// attempt number, block = site / 32 and mask = the one bit of the site), mask = the accepted sites
+// of the block.  Within a block of a sweep the sites are visited in ascending order, so the hash
+// pins the complete spin sequence.  The host replay (oracle/osa_oracle.c) computes the same value.
+constexpr unsigned long long TRACE_OFFSET = 0xcbf29ce484222325ull, TRACE_PRIME = 0x100000001b3ull;
+__host__ __device__ __forceinline__ unsigned long long trace_step(unsigned long long h, uint32_t step,
+                                                                  uint32_t block, uint32_t mask) {
+  h = (h ^ (unsigned long long)step) * TRACE_PRIME;
+  return (h ^ (((unsigned long long)block << 32) | mask)) * TRACE_PRIME;
+}
+
 template <typename T>
 __device__ __forceinline__ void vec_unpack(const typename Vec16<T>::type &v, T *out);
 template <>
@@ -120,6 +134,16 @@ __device__ __forceinline__ void vec_unpack<float>(const float4 &v, float *o) {
 template <>
 __device__ __forceinline__ void vec_unpack<double>(const double2 &v, double *o) {
   o[0] = v.x; o[1] = v.y;
+}
+template <typename T>
+__device__ __forceinline__ typename Vec16<T>::type vec_pack(const T *v);
+template <>
+__device__ __forceinline__ float4 vec_pack<float>(const float *v) {
+  return make_float4(v[0], v[1], v[2], v[3]);
+}
+template <>
+__device__ __forceinline__ double2 vec_pack<double>(const double *v) {
+  return make_double2(v[0], v[1]);
 }
 
 // ---------------------------------------------------------------------------
@@ -190,6 +214,9 @@ struct SparseParams {
   int debug_flags;        // timing experiments only (tools/probe.py): 1 = skip best-state snapshots
   int nw;
   Counters *counters;
+  unsigned long long *trace_hash;  // optional [num_tries], see trace_step()
+  // optional [ceil(n/32)]: bit g of word b = sites 32b+4g .. 32b+4g+3 are pairwise non-adjacent
+  const uint32_t *indep;
 };
 
 // Timing-experiment switches that make the results of a call meaningless (skipped row streaming,

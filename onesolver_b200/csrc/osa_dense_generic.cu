@@ -47,15 +47,35 @@ __global__ void k_dense_generic(const DenseParams<T> p, int n_pad, int per_warp_
     *reinterpret_cast<VecT *>(h + j) = *reinterpret_cast<const VecT *>(p.diag + j);
   __syncwarp();
 
+  // h += sgn * Q[k,:]: 16-byte loads of the row (L2) and of h (shared memory), eight in flight per
+  // lane, 16-byte stores of h
   auto add_row = [&](int k, T sgn) {
     const T *row = p.qoff + (size_t)k * p.ld;
-    for (int j = lane * V; j < n_pad; j += 32 * V) {
-      const VecT q = __ldg(reinterpret_cast<const VecT *>(row + j));
-      T qv[V], hv[V];
-      vec_unpack<T>(q, qv);
-      vec_unpack<T>(*reinterpret_cast<const VecT *>(h + j), hv);
+    constexpr int U = 8;
+    int j = lane * V;
+    for (; j + (U - 1) * 32 * V < n_pad; j += U * 32 * V) {
+      VecT q[U];
 #pragma unroll
-      for (int e = 0; e < V; ++e) h[j + e] = det::fma(sgn, qv[e], hv[e]);
+      for (int u = 0; u < U; ++u) q[u] = __ldg(reinterpret_cast<const VecT *>(row + j + u * 32 * V));
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        T qv[V], hv[V];
+        vec_unpack<T>(q[u], qv);
+        VecT *hp = reinterpret_cast<VecT *>(h + j + u * 32 * V);
+        vec_unpack<T>(*hp, hv);
+#pragma unroll
+        for (int e = 0; e < V; ++e) hv[e] = det::fma(sgn, qv[e], hv[e]);
+        *hp = vec_pack<T>(hv);
+      }
+    }
+    for (; j < n_pad; j += 32 * V) {
+      T qv[V], hv[V];
+      vec_unpack<T>(__ldg(reinterpret_cast<const VecT *>(row + j)), qv);
+      VecT *hp = reinterpret_cast<VecT *>(h + j);
+      vec_unpack<T>(*hp, hv);
+#pragma unroll
+      for (int e = 0; e < V; ++e) hv[e] = det::fma(sgn, qv[e], hv[e]);
+      *hp = vec_pack<T>(hv);
     }
   };
 
@@ -71,10 +91,12 @@ __global__ void k_dense_generic(const DenseParams<T> p, int n_pad, int per_warp_
 
   double erel = 0.0, best = 0.0;
   bool at_best = true;
+  unsigned long long trace = TRACE_OFFSET;  // flip trace, see osa_common.cuh
 
-  // walk one batch of <=32 attempts (lane l: site_l, theta_l, active)
-  auto run_batch = [&](int site_l, T theta_l, bool active) {
-    uint32_t from = 0xffffffffu;
+  // walk one batch of <=32 attempts (lane l: site_l, theta_l, active).  Sequential mode: the
+  // batch is block `blk` of sweep `step`; random-site mode (blk < 0): lane l is attempt step + l.
+  auto run_batch = [&](int site_l, T theta_l, bool active, uint32_t step, int blk) {
+    uint32_t from = 0xffffffffu, accepted = 0u;
     for (;;) {
       __syncwarp();
       uint32_t xl = 0;
@@ -105,8 +127,11 @@ __global__ void k_dense_generic(const DenseParams<T> p, int n_pad, int per_warp_
       if (lane == 0) x[k >> 5] ^= (1u << (k & 31));
       add_row(k, xk ? (T)-1 : (T)1);
       ++cnt_acc;
+      accepted |= 1u << s;
+      if (blk < 0) trace = trace_step(trace, step + (uint32_t)s, (uint32_t)k >> 5, 1u << (k & 31));
       from = (s == 31) ? 0u : (0xffffffffu << (s + 1));
     }
+    if (blk >= 0 && accepted != 0u) trace = trace_step(trace, step, (uint32_t)blk, accepted);
   };
 
   if (p.mode == OSA_MODE_SEQUENTIAL_SWEEP) {
@@ -118,7 +143,7 @@ __global__ void k_dense_generic(const DenseParams<T> p, int n_pad, int per_warp_
           const int site = i0 + lane;
           const U4 d = engine_draw(p.seed, traj, STREAM_SEQ, (uint32_t)site >> 2, step);
           const T theta = threshold<T>(ts, pick(d, (uint32_t)site & 3u));
-          run_batch(site, theta, site < n);
+          run_batch(site, theta, site < n, step, i0 >> 5);
         }
       }
     }
@@ -136,7 +161,7 @@ __global__ void k_dense_generic(const DenseParams<T> p, int n_pad, int per_warp_
         site = (int)__umulhi(d.x, (uint32_t)n);  // bit_index(), annealing.hpp:101
         theta = threshold<T>(ts, d.y);
       }
-      run_batch(site, theta, active);
+      run_batch(site, theta, active, (uint32_t)s0, -1);
     }
   }
 
@@ -147,6 +172,7 @@ __global__ void k_dense_generic(const DenseParams<T> p, int n_pad, int per_warp_
   for (int k = lane; k < nw; k += 32) p.best_states[tl * (uint64_t)nw + k] = xb[k];
   if (lane == 0) {
     p.best_rel[tl] = best;
+    if (p.trace_hash) p.trace_hash[tl] = trace;
     atomicAdd(&p.counters->accepts, cnt_acc);
     atomicAdd(&p.counters->row_fetches, cnt_acc);
     atomicAdd(&p.counters->init_row_fetches, cnt_init);

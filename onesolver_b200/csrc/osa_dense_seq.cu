@@ -141,11 +141,13 @@ __global__ void __launch_bounds__(TH, 1) k_dense_seq(const DenseParams<T> p) {
   // ---- annealing ----
   double erel[TPW], best[TPW];
   bool at_best[TPW];
+  unsigned long long trace[TPW];  // flip trace, see osa_common.cuh
 #pragma unroll
   for (int rr = 0; rr < TPW; ++rr) {
     erel[rr] = 0.0;
     best[rr] = 0.0;
     at_best[rr] = true;
+    trace[rr] = TRACE_OFFSET;
   }
 
   uint32_t step = 0;
@@ -216,6 +218,7 @@ __global__ void __launch_bounds__(TH, 1) k_dense_seq(const DenseParams<T> p) {
               sg |= (xbit << s);
               from = (s == 31) ? 0u : (0xffffffffu << (s + 1));
             }
+            if (acc != 0u) trace[rr] = trace_step(trace[rr], step, (uint32_t)b, acc);
             if (lane == 0) {
               s_x[r][b] = xw;
               s_acc[r] = acc;
@@ -258,6 +261,7 @@ __global__ void __launch_bounds__(TH, 1) k_dense_seq(const DenseParams<T> p) {
       const uint64_t tl = batch0 + (uint64_t)r;
       for (int k = lane; k < p.nw; k += 32) p.best_states[tl * (uint64_t)p.nw + k] = s_xb[r][k];
       if (lane == 0) p.best_rel[tl] = best[rr];
+      if (lane == 0 && p.trace_hash) p.trace_hash[tl] = trace[rr];
     }
   }
   if (lane == 0 && cnt_acc) atomicAdd(&p.counters->accepts, cnt_acc);

@@ -258,10 +258,11 @@ __global__ void __launch_bounds__(WsRegs<DW>::THREADS, 1) k_dense_seq_ws(const D
     const bool lead = has && seg == 0;
     const int c0 = seg * HS;
     uint32_t pa = 0u, ps = 0u;  // accept / sign masks of the previous block (every lane of r)
+    unsigned long long trace = TRACE_OFFSET;  // flip trace of trajectory r (lead lane), osa_common.cuh
     long long t_decide = 0, t_catch = 0, t_sites = 0;  // the last two only with debug flag 8
 
     // decision of block j of the schedule (block b of the sweep) for the trajectories of this warp
-    auto walk = [&](long long j, int b) {
+    auto walk = [&](long long j, int b, uint32_t step) {
       const int par = (int)(j & 1);
       const int i0 = b * 32;
       const uint32_t xw0 = sh.x[b][rr];
@@ -389,6 +390,7 @@ __global__ void __launch_bounds__(WsRegs<DW>::THREADS, 1) k_dense_seq_ws(const D
         sh.x[b][r] = xw0 ^ acc;
         s_acc[par][r] = acc;
         s_sign[par][r] = acc & xw0;  // spins that were 1 before their flip: sign -1
+        if (acc != 0u) trace = trace_step(trace, step, (uint32_t)b, acc);
         const uint32_t na = sh.naccept[r] + (uint32_t)__popc(acc);
         sh.naccept[r] = na;
         if (na >= 0x80000000u) {
@@ -412,10 +414,11 @@ __global__ void __launch_bounds__(WsRegs<DW>::THREADS, 1) k_dense_seq_ws(const D
     {
       int b = 0;
       for (long long j = 0; j < total_blocks; ++j) {
+        const uint32_t step = nxt.step;  // sweep number of block j
         advance(nxt);
         const bool more = j + 1 < total_blocks;
         if (more) prepare_tiles(nxt, (int)((j + 1) & 1));
-        const long long t0 = walk(j, b);
+        const long long t0 = walk(j, b, step);
         b = (b + 1 == nblk) ? 0 : b + 1;
         if (more) prepare_thresholds(nxt, (int)((j + 1) & 1));
         t_decide += clock64() - t0;
@@ -433,6 +436,7 @@ __global__ void __launch_bounds__(WsRegs<DW>::THREADS, 1) k_dense_seq_ws(const D
     }
     if (dt < R && sh.naccept[dt])
       atomicAdd(&p.counters->accepts, (unsigned long long)sh.naccept[dt]);
+    if (p.trace_hash && lead && tv) p.trace_hash[batch0 + (uint64_t)r] = trace;
     if (dt == 0) {
       atomicAdd(&p.counters->cyc_decide, (unsigned long long)t_decide);
       if (p.debug_flags & 8) {  // walk phases of decide warp 0 instead of the apply-role timers

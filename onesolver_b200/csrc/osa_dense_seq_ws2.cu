@@ -75,7 +75,6 @@ struct FlowRing {
   static_assert(KE >= 3, "row ring too small");
 };
 
-constexpr unsigned long long FNV_OFFSET = 0xcbf29ce484222325ull, FNV_PRIME = 0x100000001b3ull;
 
 template <typename T, int NCH, int R, int K, int G, bool PT>
 __global__ void __launch_bounds__(WsRegs<FLOW_DW>::THREADS, 1) k_dense_seq_flow(const DenseParams<T> p) {
@@ -302,7 +301,7 @@ __global__ void __launch_bounds__(WsRegs<FLOW_DW>::THREADS, 1) k_dense_seq_flow(
     double erel = 0.0, best = 0.0;                   // energy relative to the start: now / best
     bool at_best = true;
     uint32_t naccept = 0u;
-    unsigned long long trace = FNV_OFFSET;
+    unsigned long long trace = TRACE_OFFSET;
 
     // thresholds of block c for the sites of this warp's trajectories, into th[]: lane (t, g)
     // draws the Philox block of sites 4g..4g+3 of trajectory slot t (STREAM_SEQ: c0 = site >> 2),
@@ -487,10 +486,7 @@ __global__ void __launch_bounds__(WsRegs<FLOW_DW>::THREADS, 1) k_dense_seq_flow(
           copy = true;  // the first flip of the block left the best state
           at_best = false;
         }
-        if (my_acc != 0u) {  // flip trace: FNV-1a over (sweep, block, accept mask) of the blocks with flips
-          trace = (trace ^ (unsigned long long)cur.step) * FNV_PRIME;
-          trace = (trace ^ (((unsigned long long)(uint32_t)b << 32) | my_acc)) * FNV_PRIME;
-        }
+        if (my_acc != 0u) trace = trace_step(trace, cur.step, (uint32_t)b, my_acc);
         naccept += (uint32_t)__popc(my_acc);
         if (naccept >= 0x80000000u) {
           atomicAdd(&p.counters->accepts, (unsigned long long)naccept);

@@ -26,6 +26,7 @@ struct osa_problem {
   void *d_val = nullptr;      // sweep precision
   double *d_val64 = nullptr;
   double *d_diag64 = nullptr;
+  uint32_t *d_indep = nullptr;  // [ceil(n/32)] groups of four pairwise non-adjacent sites (k_sparse)
   // execution
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -37,6 +38,8 @@ struct osa_problem {
   size_t cap_states_words = 0;
   uint32_t *d_xbest_ws = nullptr;
   size_t cap_ws_words = 0;
+  unsigned long long *d_trace = nullptr;  // [cap_trace] flip-trace hashes (osa_anneal_traced)
+  size_t cap_trace = 0;
   void *d_tscale = nullptr;
   size_t cap_tscale_bytes = 0;
   osa::Counters *d_counters = nullptr;

@@ -77,6 +77,7 @@ __global__ void k_sparse(const SparseParams<T> p, int x_words_per_warp) {
   __syncwarp();
 
   double erel = 0.0, best = 0.0;
+  unsigned long long trace = TRACE_OFFSET;  // flip trace, see osa_common.cuh
   bool at_best = true;   // the current state IS the best state
   bool mat = false;      // XB holds the best state explicitly (no log needed)
   int log_len = 0;       // flips since the best state was left (valid while !at_best && !mat)
@@ -181,16 +182,68 @@ __global__ void k_sparse(const SparseParams<T> p, int x_words_per_warp) {
           // one Philox block serves four consecutive sites: their four thresholds (a chain of
           // ~40 dependent operations each) are computed together so the chains overlap, and sit
           // off the critical path of three of the four site steps
+          uint32_t blk_acc = 0u;  // sites of this block that this lane's trajectory flipped
+          const uint32_t indep = p.indep ? __ldg(p.indep + b) : 0u;
+          // decision of site i (field hk in hand): accept test, bookkeeping, spin update
+          auto decide = [&](int s, int i, T hk, T theta) {
+            const uint32_t xiw = X[i];
+            const T dE = ((xiw >> lane) & 1u) ? -hk : hk;
+            const bool acc = tv && (dE < theta);
+            const bool overflow = acc ? track(i, dE) : false;
+            const uint32_t spill = __ballot_sync(0xffffffffu, overflow);
+            if (spill) {
+              materialize(spill, true);
+              if (overflow) mat = true;
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, acc);
+            if (acc) blk_acc |= 1u << s;
+            if (bal) {
+              __syncwarp();
+              if (lane == 0) X[i] = xiw ^ bal;
+              __syncwarp();
+            }
+          };
           for (int s4 = 0; s4 < i_end; s4 += 4) {
             d = engine_draw(p.seed, traj, STREAM_SEQ, (uint32_t)(b * 32 + s4) >> 2, step);
             const T th4[4] = {threshold<T>(ts, d.x), threshold<T>(ts, d.y), threshold<T>(ts, d.z),
                               threshold<T>(ts, d.w)};
+            if (staged && e1 > e0 && s4 + 4 <= i_end && ((indep >> (s4 >> 2)) & 1u)) {
+              // The four sites are pairwise non-adjacent (precomputed per block at problem
+              // creation), so none of their flips changes the field of another: the four
+              // neighbour gathers are independent chains and run side by side, the decisions
+              // follow in site order.  Rows are padded to the longest of the four with +0.0
+              // (h + 0 = h), the additions of a row stay in CSR order -- the same bits as the
+              // one-site-at-a-time path below.
+              const int32_t *sc = stage->col[buf] - e0;
+              const T *sv = stage->val[buf] - e0;
+              int pb[4], pe[4];
+              T hk[4];
+              int len = 0;
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {
+                pb[k4] = __shfl_sync(0xffffffffu, rp_lo, s4 + k4);
+                pe[k4] = __shfl_sync(0xffffffffu, rp_hi, s4 + k4);
+                hk[k4] = __shfl_sync(0xffffffffu, dg, s4 + k4);
+                len = max(len, pe[k4] - pb[k4]);
+              }
+              for (int t = 0; t < len; ++t) {
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                  const int q = pb[k4] + t;
+                  const int qc = min(q, e1 - 1);
+                  const T v = q < pe[k4] ? sv[qc] : (T)0;
+                  if ((X[sc[qc]] >> lane) & 1u) hk[k4] = det::add(hk[k4], v);
+                }
+              }
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) decide(s4 + k4, b * 32 + s4 + k4, hk[k4], th4[k4]);
+              continue;
+            }
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
               const int s = s4 + k4;
               if (s >= i_end) break;
               const int i = b * 32 + s;
-              const T theta = th4[k4];
               const int pb = __shfl_sync(0xffffffffu, rp_lo, s);
               const int pe = __shfl_sync(0xffffffffu, rp_hi, s);
               T hk = __shfl_sync(0xffffffffu, dg, s);
@@ -208,23 +261,10 @@ __global__ void k_sparse(const SparseParams<T> p, int x_words_per_warp) {
                   if ((X[c] >> lane) & 1u) hk = det::add(hk, v);
                 }
               }
-              const uint32_t xiw = X[i];
-              const T dE = ((xiw >> lane) & 1u) ? -hk : hk;
-              const bool acc = tv && (dE < theta);
-              const bool overflow = acc ? track(i, dE) : false;
-              const uint32_t spill = __ballot_sync(0xffffffffu, overflow);
-              if (spill) {
-                materialize(spill, true);
-                if (overflow) mat = true;
-              }
-              const uint32_t bal = __ballot_sync(0xffffffffu, acc);
-              if (bal) {
-                __syncwarp();
-                if (lane == 0) X[i] = xiw ^ bal;
-                __syncwarp();
-              }
+              decide(s, i, hk, th4[k4]);
             }
           }
+          if (blk_acc != 0u) trace = trace_step(trace, step, (uint32_t)b, blk_acc);
           rp_lo = nrp_lo;
           rp_hi = nrp_hi;
           dg = ndg;
@@ -257,7 +297,10 @@ __global__ void k_sparse(const SparseParams<T> p, int x_words_per_warp) {
         if (overflow) mat = true;
       }
       __syncwarp();
-      if (acc) atomicXor(&X[k], 1u << lane);
+      if (acc) {
+        atomicXor(&X[k], 1u << lane);
+        trace = trace_step(trace, (uint32_t)st, (uint32_t)k >> 5, 1u << (k & 31));
+      }
       __syncwarp();
     }
   }
@@ -280,6 +323,7 @@ __global__ void k_sparse(const SparseParams<T> p, int x_words_per_warp) {
       p.best_states[tl * (uint64_t)p.nw + k] = word;
     }
     p.best_rel[tl] = best;
+    if (p.trace_hash) p.trace_hash[tl] = trace;
   }
   // warp-reduce the accept counter
   for (int o = 16; o > 0; o >>= 1) cnt_acc += __shfl_down_sync(0xffffffffu, cnt_acc, o);

@@ -41,6 +41,8 @@ def load():
     P = ctypes.POINTER
     lib.orc_philox4x32_10.argtypes = [vp, vp, vp]
     lib.orc_engine_draw.argtypes = [u64, u64, u32, u32, u32, vp]
+    lib.orc_set_trace_output.argtypes = [vp]
+    lib.orc_set_trace_output.restype = None
     lib.orc_neglogf.argtypes = [u32]
     lib.orc_neglogf.restype = ctypes.c_float
     lib.orc_init_bit.argtypes = [u64, u64, u32]
@@ -155,6 +157,24 @@ def tscale(schedule, accept_rule, dtype):
     s = np.asarray(schedule, dtype=np.float64)
     t = s if accept_rule == 0 else 1.0 / s
     return np.ascontiguousarray(t.astype(dtype))
+
+
+class _Trace:
+    """with _Trace(n) as t: ... replay ...; t.hashes = flip traces of the n trajectories."""
+
+    def __init__(self, num_tries):
+        self.hashes = np.zeros(num_tries, dtype=np.uint64)
+
+    def __enter__(self):
+        load().orc_set_trace_output(ctypes.c_void_p(self.hashes.ctypes.data))
+        return self
+
+    def __exit__(self, *exc):
+        load().orc_set_trace_output(None)
+
+
+def trace(num_tries):
+    return _Trace(num_tries)
 
 
 def replay_dense(qsym, schedule, num_iter, num_tries, sweeps_per_beta=1, mode=0, accept_rule=0,

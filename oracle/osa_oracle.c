@@ -297,6 +297,37 @@ void orc_energy_packed(const double *qsym, int n, const uint32_t *states_packed,
 /* (B) bit-exact host replay                                                 */
 /* ------------------------------------------------------------------------- */
 
+/* Flip trace of a trajectory, the value osa_anneal_traced returns (include/onesolver_b200.h):
+ * FNV-1a over (step, block of 32 sites, mask of accepted sites) of every block with an accepted
+ * flip, in the order the flips happen.  orc_set_trace_output(buf) makes the replays below store
+ * the hash of trajectory tl in buf[tl] (NULL switches it off again).                           */
+static uint64_t *g_trace_out = NULL;
+void orc_set_trace_output(uint64_t *buf) { g_trace_out = buf; }
+
+typedef struct {
+  uint64_t h;
+  uint32_t step, blk, mask;
+} orc_trace;
+
+static inline void trace_init(orc_trace *t) {
+  t->h = 0xcbf29ce484222325ull;
+  t->step = t->blk = t->mask = 0;
+}
+static inline void trace_flush(orc_trace *t) {
+  if (t->mask) {
+    t->h = (t->h ^ (uint64_t)t->step) * 0x100000001b3ull;
+    t->h = (t->h ^ (((uint64_t)t->blk << 32) | t->mask)) * 0x100000001b3ull;
+  }
+  t->mask = 0;
+}
+static inline void trace_flip(orc_trace *t, uint32_t step, int site) {
+  const uint32_t blk = (uint32_t)site >> 5;
+  if (t->mask && (t->step != step || t->blk != blk)) trace_flush(t);
+  t->step = step;
+  t->blk = blk;
+  t->mask |= 1u << (site & 31);
+}
+
 static inline int getbit(const uint32_t *x, int i) { return (int)((x[i >> 5] >> (i & 31)) & 1u); }
 static inline void flipbit(uint32_t *x, int i) { x[i >> 5] ^= (1u << (i & 31)); }
 
@@ -368,6 +399,8 @@ static void init_state_packed(uint64_t seed, uint64_t traj, int n, uint32_t *x) 
         double erel = 0.0, best = 0.0;                                                           \
         uint64_t sidx = 0;                                                                       \
         uint32_t step = step_base;                                                               \
+        orc_trace tr;                                                                            \
+        trace_init(&tr);                                                                         \
         for (int iter = 0; iter < num_iter; ++iter) {                                            \
           const T ts = tscale_traj ? tscale_traj[tl] : tscale[iter];                             \
           for (int sw = 0; sw < sweeps_per_beta; ++sw, ++step) {                                 \
@@ -393,6 +426,7 @@ static void init_state_packed(uint64_t seed, uint64_t traj, int n, uint32_t *x) 
                 const T *row = qoff + (size_t)k * ld;                                            \
                 for (int j = 0; j < n; ++j) h[j] = FMA(sgn, row[j], h[j]);                       \
                 flipbit(x, k);                                                                   \
+                trace_flip(&tr, step, k);                                                        \
                 erel += (double)dE;                                                              \
                 tot_acc++;                                                                       \
                 if (any) any[sidx] = 1;                                                          \
@@ -405,6 +439,8 @@ static void init_state_packed(uint64_t seed, uint64_t traj, int n, uint32_t *x) 
           }                                                                                      \
         }                                                                                        \
         best_rel[tl] = best;                                                                     \
+        trace_flush(&tr);                                                                        \
+        if (g_trace_out) g_trace_out[tl] = tr.h;                                                 \
         if (best_states_packed) memcpy(best_states_packed + (size_t)tl * nw, xb, sizeof(uint32_t) * (size_t)nw); \
         if (final_states_packed) memcpy(final_states_packed + (size_t)tl * nw, x, sizeof(uint32_t) * (size_t)nw); \
       }                                                                                          \
@@ -448,6 +484,8 @@ DEFINE_REPLAY_DENSE(orc_replay_dense_f64, double, fma)
       memcpy(xb, x, sizeof(uint32_t) * (size_t)nw);                                              \
       double erel = 0.0, best = 0.0;                                                             \
       uint32_t step = 0;                                                                         \
+      orc_trace tr;                                                                              \
+      trace_init(&tr);                                                                           \
       for (int iter = 0; iter < num_iter; ++iter) {                                              \
         const T ts = tscale[iter];                                                               \
         for (int sw = 0; sw < sweeps_per_beta; ++sw, ++step) {                                   \
@@ -474,6 +512,7 @@ DEFINE_REPLAY_DENSE(orc_replay_dense_f64, double, fma)
             const T dE = xk ? -hk : hk;                                                          \
             if (dE < theta) {                                                                    \
               flipbit(x, k);                                                                     \
+              trace_flip(&tr, step, k);                                                          \
               erel += (double)dE;                                                                \
               tot_acc++;                                                                         \
               if (erel < best) {                                                                 \
@@ -484,6 +523,8 @@ DEFINE_REPLAY_DENSE(orc_replay_dense_f64, double, fma)
           }                                                                                      \
         }                                                                                        \
       }                                                                                          \
+      trace_flush(&tr);                                                                          \
+      if (g_trace_out) g_trace_out[tl] = tr.h;                                                   \
       best_rel[tl] = best;                                                                       \
       if (best_states_packed) memcpy(best_states_packed + (size_t)tl * nw, xb, sizeof(uint32_t) * (size_t)nw); \
       if (final_states_packed) memcpy(final_states_packed + (size_t)tl * nw, x, sizeof(uint32_t) * (size_t)nw); \

@@ -102,6 +102,11 @@ typedef struct {
   uint64_t init_row_fetches; /* (batch, site) pairs with >= 1 set initial spin */
 } orc_counters;
 
+/* The replays below store the flip trace of trajectory tl (the value of osa_anneal_traced, see
+ * include/onesolver_b200.h) in buf[tl] while buf is set; NULL switches it off.  Not thread-safe
+ * across concurrent replay CALLS (the calls themselves are OpenMP-parallel inside).           */
+void orc_set_trace_output(uint64_t *buf);
+
 /* Dense replay.  qoff: n*ld row-major symmetric with ZERO diagonal, diag: n.
  * tscale[num_iter]: threshold scale per iteration (beta for the reference rule,
  * 1/beta for the Boltzmann rule), already rounded to the sweep precision.

@@ -29,6 +29,24 @@ def test_default_workload_is_baseline_config5_share():
     assert len(sched) == 32 and np.isclose(sched[0], 1.28)
 
 
+def test_headline_workload_constants_are_frozen(monkeypatch):
+    """attempts/s depends on the schedule (accept fraction), and BASELINE.json fixes
+    neither sweeps nor beta -- the round-1 choice is the contract from here on.  Any change of these
+    defaults voids the round-over-round comparison, so it has to fail a test first."""
+    monkeypatch.setattr(sys, "argv", ["bench.py"])
+    a = bench.parse_args()
+    assert (a.n, a.tries_per_gpu, a.sweeps, a.precision) == (4096, 131072, 32, "f32")
+    assert (a.beta_min, a.beta_max, a.workload, a.impl) == (1.28, 19.2, "config5", "engine")
+    assert a.warmup >= 3 and a.gpus == 1
+    sched = bench.make_schedule(a)
+    assert len(sched) == 32 and sched[0] == 1.28 and abs(sched[-1] - 19.2) < 1e-9
+    ratio = sched[1:] / sched[:-1]
+    assert np.allclose(ratio, ratio[0])  # geometric, one-solver-anneal.cpp:31-39
+    cfg = bench.config_dict(a, 1)
+    assert cfg["mode"] == "sequential_sweep" and cfg["accept_rule"] == "reference"
+    assert cfg["seed"] == 1234 and cfg["sweep_precision"] == "f32"
+
+
 def test_config3_and_config4_specs_match_baseline_shapes():
     s3 = bench.other_config_spec(_args(workload="config3"))
     assert (s3["n"], s3["tries"], s3["sweeps"], s3["dtype"]) == (1024, 16384, 1000, "f64")

@@ -82,6 +82,36 @@ def test_config5_dense_n4096_131072_tries_per_gpu(gpu):
     assert (unpack_states(res.best_states_packed[res.index], n)[0] == res.state).all()
 
 
+def test_config5_bench_schedule_replayed_from_the_middle_of_the_id_range(gpu):
+    """The bench workload itself (bench.py defaults: 32 sweeps, geometric beta 1.28 -> 19.2,
+    131072 tries, fp32 fields), and two whole CTAs' worth of trajectories from the MIDDLE of the id
+    range replayed on the host: flip traces (the complete spin sequence), best states, energies."""
+    import argparse
+    import bench
+    a = argparse.Namespace(n=4096, sweeps=32, beta_min=1.28, beta_max=19.2)
+    n, tries = 4096, 131072
+    q = bench.make_instance(n)
+    sched = bench.make_schedule(a)
+    with Problem.dense(q, sweep_precision=capi.SWEEP_F32) as prob:
+        res = prob.anneal(sched, 32, tries, mode=capi.MODE_SEQUENTIAL_SWEEP, want_energies=True,
+                          want_states=True, want_trace=True)
+    check_common(res, tries)
+    assert res.stats["attempts"] == tries * n * 32
+    assert abs(res.stats["accepts"] / res.stats["attempts"] - 0.171) < 0.005  # the frozen workload
+    r = res.stats["traj_per_batch"]
+    first = (tries // 2 // r) * r  # a batch boundary in the middle
+    with ob.trace(2 * r) as tr:
+        _, best, _, _ = ob.replay_dense(q, sched, 32, 2 * r, mode=1, first_try=first,
+                                        dtype=np.float32, batch_r=r)
+    np.testing.assert_array_equal(res.trace_hash[first:first + 2 * r], tr.hashes)
+    np.testing.assert_array_equal(res.best_states_packed[first:first + 2 * r], best)
+    e_ref = ob.energy_packed(q, best)
+    np.testing.assert_allclose(res.best_energies[first:first + 2 * r], e_ref, rtol=REL)
+    # fp32 sweep, energies re-scored in fp64: north_star's 1e-5 bar for fp32 is met with room
+    e_win = ob.ref_energy(q, res.state.astype(np.int8))
+    assert abs(e_win - res.energy) <= REL * abs(e_win)
+
+
 def test_config4_sparse_n5627_65536_tries_linear_schedule(gpu):
     """BASELINE config 4 shape: sparse degree<=15 QUBO on N=5627 (CSR), 65536 tries, linear schedule."""
     n, tries, sweeps = 5627, 65536, 3

@@ -32,11 +32,15 @@ def run_and_compare_dense(q, sched, num_iter, num_tries, mode, dtype, spb=1, ker
     with Problem.dense(q, sweep_precision=prec) as prob:
         res = prob.anneal(sched, num_iter, num_tries, sweeps_per_beta=spb, mode=mode,
                           accept_rule=accept_rule, kernel_variant=kernel, first_try=first_try,
-                          seed=seed, want_energies=True, want_states=True)
+                          seed=seed, want_energies=True, want_states=True, want_trace=True)
     r = res.stats["traj_per_batch"]
-    best_rel, best, _, cnt = ob.replay_dense(q, sched, num_iter, num_tries, sweeps_per_beta=spb,
-                                             mode=mode, accept_rule=accept_rule, seed=seed,
-                                             first_try=first_try, dtype=dtype, batch_r=r)
+    with ob.trace(num_tries) as tr:
+        best_rel, best, _, cnt = ob.replay_dense(q, sched, num_iter, num_tries, sweeps_per_beta=spb,
+                                                 mode=mode, accept_rule=accept_rule, seed=seed,
+                                                 first_try=first_try, dtype=dtype, batch_r=r)
+    # the spin SEQUENCE of every trajectory (north_star criterion 2): hash of all accepted flips
+    bad = np.nonzero(res.trace_hash != tr.hashes)[0]
+    assert bad.size == 0, f"flip traces differ for {bad.size}/{num_tries} trajectories, first {bad[:8]}"
     assert_states_equal(res.best_states_packed, best, "best states vs host replay")
     assert res.stats["accepts"] == cnt.accepts
     assert res.stats["attempts"] == cnt.attempts
@@ -81,6 +85,14 @@ def test_config2_n24_matches_exhaustive_and_reference(gpu, dtype):
     ci = 3.0 * np.sqrt(max(p_ref * (1 - p_ref), 1e-4) / 4096) * np.sqrt(2)
     assert abs(p_gpu - p_ref) <= ci, (p_gpu, p_ref, ci)
     assert (res.best_energies == e_ref).mean() >= 0.98
+    # ... and on INDEPENDENT streams (other seed, disjoint trajectory ids): the two samples share
+    # nothing but the instance, so this is the statistical comparison north_star asks for.
+    # 3 sigma of the difference of two independent binomial proportions.
+    _, _, e_ind = ob.ref_anneal(q, n, sched, 400, 4096, seed=987654321, first_try=1 << 20)
+    p_ind = (e_ind == gs_energy).mean()
+    pm = 0.5 * (p_gpu + p_ind)
+    ci_ind = 3.0 * np.sqrt(max(pm * (1 - pm), 1e-4) * 2.0 / 4096)
+    assert abs(p_gpu - p_ind) <= ci_ind, (p_gpu, p_ind, ci_ind)
 
 
 def test_n24_fractional_coefficients(gpu):
@@ -205,10 +217,13 @@ def test_sparse_bit_exact(gpu, n, deg, dtype, mode, tries):
     sched = geo(iters, 0.05, 1.5)
     prec = capi.SWEEP_F32 if dtype == np.float32 else capi.SWEEP_F64
     with Problem.csr(rowptr, col, val, diag, sweep_precision=prec) as prob:
-        res = prob.anneal(sched, iters, tries, mode=mode, want_energies=True, want_states=True)
-    best_rel, best, _, cnt = ob.replay_csr(rowptr, col, val, diag, sched, iters, tries, mode=mode,
-                                           dtype=dtype)
+        res = prob.anneal(sched, iters, tries, mode=mode, want_energies=True, want_states=True,
+                          want_trace=True)
+    with ob.trace(tries) as tr:
+        best_rel, best, _, cnt = ob.replay_csr(rowptr, col, val, diag, sched, iters, tries,
+                                               mode=mode, dtype=dtype)
     assert res.stats["kernel_id"] == capi.KID_SPARSE
+    np.testing.assert_array_equal(res.trace_hash, tr.hashes)  # the spin sequence, flip by flip
     assert_states_equal(res.best_states_packed, best, "sparse best states vs host replay")
     assert res.stats["accepts"] == cnt.accepts
     q = gen.csr_to_dense(rowptr, col, val, diag)
