@@ -11,8 +11,10 @@
 #ifndef ONESOLVER_B200_MODEL_QUBO_HPP_
 #define ONESOLVER_B200_MODEL_QUBO_HPP_
 
+#include <algorithm>
 #include <cctype>
 #include <cerrno>
+#include <charconv>
 #include <cstdlib>
 #include <cstring>
 #include <istream>
@@ -47,6 +49,8 @@ public:
   QUBOModel() = default;
   QUBOModel(const Linear &c_linear, const Quadratic &c_quadratic)
       : linear(c_linear), quadratic(c_quadratic) {}
+  QUBOModel(Linear &&c_linear, Quadratic &&c_quadratic)
+      : linear(std::move(c_linear)), quadratic(std::move(c_quadratic)) {}
 
   // "QUBO model" + " i--i:v " per linear term + "i--j:v" per coupling (tests/qubo_test.cpp:54)
   std::string str() const {
@@ -113,11 +117,17 @@ struct QUBOBuilder {
     } else {
       quadratic_c.emplace(std::make_pair(i, j), coef);
     }
-    used_nodes.insert(i);
-    used_nodes.insert(j);
+    largest_node = std::max(largest_node, j);  // i <= j here
   }
-  void set_num_quadratic(int value) { num_quadratic = value; }
-  void set_num_linear(int value) { num_linear = value; }
+  // the header announces the term counts: size the maps once instead of rehashing on the way
+  void set_num_quadratic(int value) {
+    num_quadratic = value;
+    if (value > 0) quadratic_c.reserve(static_cast<std::size_t>(value));
+  }
+  void set_num_linear(int value) {
+    num_linear = value;
+    if (value > 0) linear_c.reserve(static_cast<std::size_t>(value));
+  }
   void set_max_nodes(int value) { max_nodes = value; }
 
   // checks and messages follow qubo.hpp:354-378, in the same order
@@ -137,8 +147,8 @@ struct QUBOBuilder {
     if (linear_c.size() != static_cast<std::size_t>(num_linear)) {
       throw std::invalid_argument("Number of linear terms is not equal to the declared one.");
     }
-    QUBOModel<int, double> model(linear_c, quadratic_c);
-    model.set_nodes(*used_nodes.rbegin() + 1);  // N = largest index seen + 1
+    QUBOModel<int, double> model(std::move(linear_c), std::move(quadratic_c));
+    model.set_nodes(largest_node + 1);  // N = largest index seen + 1
     return model;
   }
 
@@ -146,7 +156,7 @@ private:
   LinearCoef<int, double> linear_c;
   QuadraticCoef<int, double> quadratic_c;
   int num_quadratic = -1, num_linear = -1, max_nodes = -1;
-  std::set<int> used_nodes;
+  int largest_node = -1;
 };
 
 namespace detail {
@@ -252,10 +262,19 @@ private:
       if (r < s.size() && (s[r] == '+' || s[r] == '-')) ++r;
       if (digits(r)) end = r;  // otherwise the 'e' is left for the line-end check to reject
     }
+    out = end;
+    if (numeric) {
+      // plain decimal: std::from_chars on the validated extent (correctly rounded like strtod,
+      // no copy of the token); it takes '-' but not '+'
+      const char *first = s.data() + p, *last = s.data() + end;
+      if (*first == '+') ++first;
+      const auto res = std::from_chars(first, last, value);
+      if (res.ec == std::errc() && res.ptr == last) return true;
+      // out of range etc.: strtod's answer (+-inf / denormal) below, as before
+    }
     const std::string token = s.substr(p, end - p);
     char *stop = nullptr;
     value = std::strtod(token.c_str(), &stop);
-    out = end;
     return stop != token.c_str();
   }
 
