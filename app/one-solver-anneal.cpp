@@ -9,10 +9,12 @@
 // --mode random|sweep, --accept reference|boltzmann, --sweeps-per-beta, --seed,
 // --precision f64|f32, --layout auto|dense|csr, --stats; --gpu-index K (one CUDA device) or
 // --num-gpus G (devices 0..G-1) -- without either, --device-type gpu uses every visible GPU and
-// shards the trajectories over them (osa_multi_anneal); --algorithm sa|pt with
+// shards the trajectories over them (osa_multi_anneal); --algorithm sa|pt|pa with
 // --num-replicas: parallel tempering (GPU only) -- the beta range becomes a ladder of
 // --num-replicas temperatures (built by the chosen schedule type), --num-iter counts rounds,
-// --sweeps-per-beta the sweeps per round and --num-tries the independent ladders.
+// --sweeps-per-beta the sweeps per round and --num-tries the independent ladders; population
+// annealing (GPU only) -- the schedule of --num-iter temperatures is walked by --num-tries
+// populations of --num-replicas replicas, resampled between the temperatures.
 #include <vector>
 
 #include "cli_common.hpp"
@@ -49,8 +51,10 @@ void declare_options(cli::Options &options) {
       .add("gpu-index", true, "", "use this CUDA device only (default: every visible GPU)")
       .add("num-gpus", true, "", "use CUDA devices 0..N-1 (default: every visible GPU)")
       .add("stats", false, "", "print engine statistics (gpu)")
-      .add("algorithm", true, "sa", "sa (simulated annealing) or pt (parallel tempering, gpu)")
-      .add("num-replicas", true, "12", "temperatures per ladder with --algorithm pt");
+      .add("algorithm", true, "sa",
+           "sa (simulated annealing), pt (parallel tempering, gpu) or pa (population annealing, gpu)")
+      .add("num-replicas", true, "12",
+           "temperatures per ladder with --algorithm pt, replicas per population with pa");
 }
 
 // validation order and messages of the reference (one-solver-anneal.cpp:78-115), then our extras
@@ -75,7 +79,7 @@ Settings read_settings(const cli::Options &options) {
       cli::checked_choice(options, "accept", {"reference", "boltzmann"}, "acceptance rule");
   const std::string precision = cli::checked_choice(options, "precision", {"f64", "f32"}, "precision");
   const std::string layout = cli::checked_choice(options, "layout", {"auto", "dense", "csr"}, "layout");
-  s.algorithm = cli::checked_choice(options, "algorithm", {"sa", "pt"}, "algorithm");
+  s.algorithm = cli::checked_choice(options, "algorithm", {"sa", "pt", "pa"}, "algorithm");
   s.num_replicas = static_cast<unsigned int>(options.uint("num-replicas"));
   if (s.algorithm == "pt" && s.num_replicas < 2)
     cli::usage_error("Parallel tempering needs at least two replicas");
@@ -95,7 +99,9 @@ Settings read_settings(const cli::Options &options) {
     if (g < 1) cli::usage_error("--num-gpus must be at least 1");
     for (int d = 0; d < g; ++d) s.gpu_devices.push_back(d);
   }
-  if (s.algorithm == "pt" && s.gpu_devices.empty()) s.gpu_devices = {0};  // one device per ladder set
+  if (s.algorithm == "pa" && s.num_replicas < 1)
+    cli::usage_error("Population annealing needs at least one replica per population");
+  if (s.algorithm != "sa" && s.gpu_devices.empty()) s.gpu_devices = {0};  // pt / pa: one device
   s.print_stats = options.count("stats");
   return s;
 }
@@ -134,12 +140,17 @@ int main(int argc, char *argv[]) {
       construct_geometric_beta_schedule(beta_schedule, s.beta_min, s.beta_max, ladder);
     }
 
+    // --algorithm pa: the schedule is the temperature ladder of a population of --num-replicas
+    // replicas, --num-tries independent populations, --sweeps-per-beta sweeps per temperature
     const qubo::Solution solution =
         tempering ? sa::parallel_tempering(instance, *device, beta_schedule,
                                            static_cast<int>(s.num_iter), s.sweeps_per_beta,
                                            s.num_tries, s.engine)
-                  : sa::anneal(instance, *device, beta_schedule, static_cast<int>(s.num_iter),
-                               s.num_tries, s.sweeps_per_beta, s.engine);
+        : s.algorithm == "pa"
+            ? sa::population_annealing(instance, *device, beta_schedule, s.sweeps_per_beta,
+                                       s.num_replicas, s.num_tries, s.engine)
+            : sa::anneal(instance, *device, beta_schedule, static_cast<int>(s.num_iter),
+                         s.num_tries, s.sweeps_per_beta, s.engine);
 
     std::ofstream results_file(s.output_file);
     solution.save(results_file);
@@ -152,6 +163,7 @@ int main(int argc, char *argv[]) {
                 << stats.ms_energy << ")" << std::endl;
       if (stats.reserved > 1) std::cout << "Devices: " << stats.reserved << std::endl;
       if (tempering) std::cout << "Replica exchanges accepted: " << stats.pt_swaps << std::endl;
+      if (s.algorithm == "pa") std::cout << "Replicas resampled: " << stats.pt_swaps << std::endl;
     }
   });
 }

@@ -87,7 +87,7 @@ typedef struct {
   int32_t reserved;
   /* diagnostics of the dense sequential kernel: SM cycles summed over CTAs (0 elsewhere) */
   uint64_t cyc_decide, cyc_apply, cyc_stage, cyc_init;
-  uint64_t pt_swaps;         /* osa_pt_anneal: accepted replica exchanges */
+  uint64_t pt_swaps;         /* osa_pt_anneal: accepted replica exchanges; osa_pa_anneal: resampled slots */
 } osa_stats;
 
 /* ---- library / device ---------------------------------------------------- */
@@ -161,6 +161,35 @@ typedef struct osa_pt_params {
 } osa_pt_params;
 
 int osa_pt_anneal(osa_problem *p, const double *betas, const osa_pt_params *params,
+                  double *best_energies, uint32_t *best_states_packed, uint8_t *best_state,
+                  double *best_energy, uint64_t *best_index, osa_stats *stats);
+
+/* ---- population annealing on top of the same sweep kernel.  The reference has no such sampler;
+ *      its benchmark report names it first among the ones it recommends
+ *      (benchmarks/annealing/performance.md:54-59).
+ * num_populations independent populations of population_size replicas; betas[num_steps] is the
+ * annealing schedule of a population.  Step t: every replica does sweeps_per_step sequential
+ * sweeps at betas[t]; then (t + 1 < num_steps) the population is resampled for the next
+ * temperature with weights exp(-(b' - b) E) from exact fp64 energies, b = the inverse temperature
+ * of the acceptance rule (1 / beta for the reference's rule, beta for the Boltzmann rule), keeping
+ * its size: systematic resampling on 40-bit integer weights with ONE uniform per (population, step)
+ * from the Philox stream, so the result does not depend on any reduction order (osa_pa.cu).
+ * Trajectory id = (first_population + population) * population_size + slot.  Dense problems with
+ * n <= 8192 (fp32 sweeps) / 4096 (fp64 sweeps) only.  Outputs as in osa_anneal, per replica slot:
+ * the best state seen in that slot.  stats->pt_swaps = replicas overwritten by a copy of another. */
+typedef struct osa_pa_params {
+  uint64_t seed;             /* 1234 like annealing.hpp:87 */
+  uint64_t first_population; /* id offset when a run is sharded over GPUs */
+  uint64_t num_populations;
+  int32_t population_size;   /* 1 .. 2^20 */
+  int32_t num_steps;         /* temperatures */
+  int32_t sweeps_per_step;
+  int32_t accept_rule;       /* OSA_ACCEPT_* */
+  uint32_t flags;            /* must be 0 */
+  int32_t reserved;
+} osa_pa_params;
+
+int osa_pa_anneal(osa_problem *p, const double *betas, const osa_pa_params *params,
                   double *best_energies, uint32_t *best_states_packed, uint8_t *best_state,
                   double *best_energy, uint64_t *best_index, osa_stats *stats);
 

@@ -246,6 +246,45 @@ qubo::Solution parallel_tempering(qubo::QUBOModel<int, T> instance, devices::que
   return qubo::Solution(state.begin(), state.end(), best_energy);
 }
 
+// Population annealing on the same sweep kernel (osa_pa_anneal).  The reference's report names it
+// first among the samplers it recommends (benchmarks/annealing/performance.md:54-59); the
+// signature follows anneal(): `betas` is the annealing schedule of a population (one temperature
+// per step), `population_size` replicas per population, `num_populations` independent populations;
+// between two temperatures a population is resampled with the Boltzmann weights of the step.
+// opt.first_try is the id of the first POPULATION.  GPU only.
+template <typename T>
+qubo::Solution population_annealing(qubo::QUBOModel<int, T> instance, devices::queue q,
+                                    const std::vector<double> &betas, int sweeps_per_step,
+                                    unsigned int population_size, unsigned int num_populations,
+                                    const Options &opt = Options()) {
+  const int N = static_cast<int>(instance.get_nodes());
+  if (N <= 0) throw std::invalid_argument("population_annealing: the model has no variables");
+  if (!q.is_gpu())
+    throw std::runtime_error(
+        "population_annealing: only --device-type gpu runs population annealing");
+  detail::ProblemGuard guard;
+  const auto flat = helpers::flatten_qubo(instance);
+  std::vector<double> flat64(flat.begin(), flat.end());
+  detail::check(osa_problem_create_dense_f64(flat64.data(), N, q.cuda_device(), opt.sweep_precision,
+                                             &guard.p),
+                "osa_problem_create_dense_f64");
+  osa_pa_params prm{};
+  prm.seed = opt.seed;
+  prm.first_population = opt.first_try;
+  prm.num_populations = num_populations;
+  prm.population_size = static_cast<std::int32_t>(population_size);
+  prm.num_steps = static_cast<std::int32_t>(betas.size());
+  prm.sweeps_per_step = sweeps_per_step;
+  prm.accept_rule = opt.accept_rule;
+  std::vector<std::uint8_t> state(N);
+  double best_energy = 0.0;
+  std::uint64_t best_index = 0;
+  detail::check(osa_pa_anneal(guard.p, betas.data(), &prm, nullptr, nullptr, state.data(),
+                              &best_energy, &best_index, opt.stats),
+                "osa_pa_anneal");
+  return qubo::Solution(state.begin(), state.end(), best_energy);
+}
+
 }  // namespace sa
 
 #endif

@@ -149,6 +149,31 @@ class Problem:
                                      ctypes.byref(st)))
         return AnnealResult(state, e.value, idx.value, st.as_dict(), energies, states)
 
+    def population_annealing(self, betas, num_populations, population_size, sweeps_per_step,
+                             seed=1234, first_population=0, accept_rule=capi.ACCEPT_BOLTZMANN,
+                             want_energies=False, want_states=False):
+        """osa_pa_anneal: num_populations independent populations of population_size replicas
+        annealed along betas with resampling between the temperatures (see the header)."""
+        lib = capi.load()
+        sched = np.ascontiguousarray(betas, dtype=np.float64)
+        tries = int(num_populations) * int(population_size)
+        prm = capi.PaParams(seed=seed, first_population=first_population,
+                            num_populations=num_populations, population_size=population_size,
+                            num_steps=int(sched.shape[0]), sweeps_per_step=sweeps_per_step,
+                            accept_rule=accept_rule, flags=0, reserved=0)
+        energies = np.empty(tries, dtype=np.float64) if want_energies else None
+        states = np.empty((tries, self.nw), dtype=np.uint32) if want_states else None
+        state = np.empty(self.n, dtype=np.uint8)
+        e = ctypes.c_double()
+        idx = ctypes.c_uint64()
+        st = capi.Stats()
+        capi.check(lib.osa_pa_anneal(self._h, sched.ctypes.data, ctypes.byref(prm),
+                                     energies.ctypes.data if want_energies else None,
+                                     states.ctypes.data if want_states else None,
+                                     state.ctypes.data, ctypes.byref(e), ctypes.byref(idx),
+                                     ctypes.byref(st)))
+        return AnnealResult(state, e.value, idx.value, st.as_dict(), energies, states)
+
     def energy_batch(self, states_packed):
         """sa::energy (annealing.hpp:31-40) of packed states, evaluated on the device."""
         lib = capi.load()

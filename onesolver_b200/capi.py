@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "osa_kernel_name", "osa_problem_create_dense_f64", "osa_problem_create_dense_f32",
     "osa_problem_create_csr_f64", "osa_problem_destroy", "osa_problem_size", "osa_anneal",
     "osa_anneal_traced",
-    "osa_pt_anneal", "osa_energy_batch", "osa_exhaustive_dense_f64", "osa_host_alloc_pinned",
+    "osa_pt_anneal", "osa_pa_anneal", "osa_energy_batch", "osa_exhaustive_dense_f64", "osa_host_alloc_pinned",
     "osa_host_free_pinned", "osa_measure_read_bandwidth",
     "osa_multi_create_dense_f64", "osa_multi_create_dense_f32", "osa_multi_create_csr_f64",
     "osa_multi_destroy", "osa_multi_devices", "osa_multi_problem", "osa_multi_anneal",
@@ -52,6 +52,20 @@ class PtParams(ctypes.Structure):
         ("num_replicas", ctypes.c_int32),
         ("num_rounds", ctypes.c_int32),
         ("sweeps_per_round", ctypes.c_int32),
+        ("accept_rule", ctypes.c_int32),
+        ("flags", ctypes.c_uint32),
+        ("reserved", ctypes.c_int32),
+    ]
+
+
+class PaParams(ctypes.Structure):
+    _fields_ = [
+        ("seed", ctypes.c_uint64),
+        ("first_population", ctypes.c_uint64),
+        ("num_populations", ctypes.c_uint64),
+        ("population_size", ctypes.c_int32),
+        ("num_steps", ctypes.c_int32),
+        ("sweeps_per_step", ctypes.c_int32),
         ("accept_rule", ctypes.c_int32),
         ("flags", ctypes.c_uint32),
         ("reserved", ctypes.c_int32),
@@ -121,6 +135,8 @@ def load():
     lib.osa_anneal_traced.argtypes = [vp, vp, P(AnnealParams), vp, vp, vp, P(ctypes.c_double), P(u64),
                                       vp, P(Stats)]
     lib.osa_pt_anneal.argtypes = [vp, vp, P(PtParams), vp, vp, vp, P(ctypes.c_double), P(u64),
+                                  P(Stats)]
+    lib.osa_pa_anneal.argtypes = [vp, vp, P(PaParams), vp, vp, vp, P(ctypes.c_double), P(u64),
                                   P(Stats)]
     lib.osa_energy_batch.argtypes = [vp, vp, u64, vp]
     lib.osa_host_alloc_pinned.argtypes = [sz, P(vp)]

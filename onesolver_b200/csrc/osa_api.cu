@@ -947,6 +947,221 @@ int osa_pt_anneal(osa_problem *p, const double *betas, const osa_pt_params *prm,
   return OSA_OK;
 }
 
+// ---------------------------------------------------------------------------
+// population annealing (osa_pa.cu): sweep -> exact energies -> resample, per temperature step
+// ---------------------------------------------------------------------------
+int osa_pa_anneal(osa_problem *p, const double *betas, const osa_pa_params *prm,
+                  double *best_energies, uint32_t *best_states_packed, uint8_t *best_state,
+                  double *best_energy, uint64_t *best_index, osa_stats *stats) {
+  if (!p || !betas || !prm) return fail(OSA_ERR_INVALID, "null argument");
+  if (prm->num_populations < 1) return fail(OSA_ERR_INVALID, "num_populations must be >= 1");
+  if (prm->population_size < 1 || prm->population_size > (1 << 20))
+    return fail(OSA_ERR_INVALID, "population_size must be in 1..2^20");
+  if (prm->num_steps < 1) return fail(OSA_ERR_INVALID, "num_steps must be >= 1");
+  if (prm->sweeps_per_step < 1) return fail(OSA_ERR_INVALID, "sweeps_per_step must be >= 1");
+  if (prm->flags != 0) return fail(OSA_ERR_INVALID, "unknown flags 0x%x", prm->flags);
+  if (prm->accept_rule != OSA_ACCEPT_REFERENCE && prm->accept_rule != OSA_ACCEPT_BOLTZMANN)
+    return fail(OSA_ERR_INVALID, "unknown accept rule %d", prm->accept_rule);
+  if ((uint64_t)prm->num_steps * (uint64_t)prm->sweeps_per_step >= (1ull << 32))
+    return fail(OSA_ERR_INVALID, "num_steps * sweeps_per_step must be < 2^32");
+  const int M = prm->population_size;
+  if (prm->num_populations > (1ull << 31) / (uint64_t)M ||
+      (prm->first_population + prm->num_populations) > (1ull << 40))
+    return fail(OSA_ERR_INVALID, "too many populations (replicas must stay below 2^31, ids below 2^40)");
+  for (int t = 0; t < prm->num_steps; ++t)
+    if (!(betas[t] > 0.0) || !std::isfinite(betas[t]))
+      return fail(OSA_ERR_INVALID, "betas[%d] = %g is not a positive finite number", t, betas[t]);
+  const bool f32 = p->prec == OSA_SWEEP_F32;
+  if (p->sparse || !dense_seq_supported(p->n, f32 ? 4 : 8))
+    return fail(OSA_ERR_UNSUPPORTED,
+                "population annealing runs on dense problems with n <= %d (this sweep precision)",
+                f32 ? 8192 : 4096);
+  const uint64_t tries = prm->num_populations * (uint64_t)M;
+  const uint64_t first_try = prm->first_population * (uint64_t)M;
+
+  DeviceGuard guard;
+  int rc = select_device(p->device);
+  if (rc) return rc;
+  rc = ensure_workspace(p, tries, 1);
+  if (rc) return rc;
+
+  const size_t esz = f32 ? 4 : 8;
+  const size_t words = (size_t)tries * p->nw;
+  uint32_t *d_cur = nullptr, *d_nxt = nullptr, *d_keep = nullptr;
+  double *d_ecur = nullptr, *d_enxt = nullptr, *d_beste = nullptr;
+  unsigned long long *d_cum = nullptr, *d_replaced = nullptr;
+  void *d_ts_traj = nullptr;
+  cudaStream_t st = p->stream;
+  auto release = [&]() {
+    dev_free(d_cur, st);
+    dev_free(d_nxt, st);
+    dev_free(d_keep, st);
+    dev_free(d_ecur, st);
+    dev_free(d_enxt, st);
+    dev_free(d_beste, st);
+    dev_free(d_cum, st);
+    dev_free(d_replaced, st);
+    dev_free((char *)d_ts_traj, st);
+  };
+#define PA_TRY(expr)                                                                        \
+  do {                                                                                      \
+    cudaError_t e_ = (expr);                                                                \
+    if (e_ != cudaSuccess) {                                                                \
+      release();                                                                            \
+      return fail(e_ == cudaErrorMemoryAllocation ? OSA_ERR_NOMEM : OSA_ERR_CUDA,           \
+                  "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), "osa_api.cu", __LINE__); \
+    }                                                                                       \
+  } while (0)
+  PA_TRY(dev_alloc(&d_cur, words * sizeof(uint32_t), st));
+  PA_TRY(dev_alloc(&d_nxt, words * sizeof(uint32_t), st));
+  PA_TRY(dev_alloc(&d_keep, words * sizeof(uint32_t), st));
+  PA_TRY(dev_alloc(&d_ecur, tries * sizeof(double), st));
+  PA_TRY(dev_alloc(&d_enxt, tries * sizeof(double), st));
+  PA_TRY(dev_alloc(&d_beste, tries * sizeof(double), st));
+  PA_TRY(dev_alloc(&d_cum, tries * sizeof(unsigned long long), st));
+  PA_TRY(dev_alloc(&d_replaced, sizeof(unsigned long long), st));
+  PA_TRY(dev_alloc((char **)&d_ts_traj, tries * esz, st));
+  {
+    std::vector<double> inf(tries, std::numeric_limits<double>::infinity());
+    PA_TRY(cudaMemcpyAsync(d_beste, inf.data(), tries * sizeof(double), cudaMemcpyHostToDevice, st));
+    PA_TRY(cudaStreamSynchronize(st));
+  }
+  PA_TRY(cudaMemsetAsync(p->d_counters, 0, sizeof(Counters), st));
+  PA_TRY(cudaMemsetAsync(d_replaced, 0, sizeof(unsigned long long), st));
+
+  LaunchInfo info = {0, 0, 0, 0};
+  int launches = 0;
+  float ms_sweep = 0.f, ms_energy = 0.f;
+  PA_TRY(cudaEventRecord(p->ev[0], st));
+  PA_TRY(launch_pt_init_states(prm->seed, first_try, tries, p->n, p->nw, d_cur, st));
+  ++launches;
+  rc = exact_energies(p, d_cur, tries, d_ecur);
+  if (rc) {
+    release();
+    return rc;
+  }
+  ++launches;
+  std::vector<unsigned char> ts_host(tries * esz);
+  for (int step = 0; step < prm->num_steps; ++step) {
+    // every replica of every population sweeps at betas[step]
+    const double ts64 = prm->accept_rule == OSA_ACCEPT_REFERENCE ? betas[step] : 1.0 / betas[step];
+    for (uint64_t t = 0; t < tries; ++t) {
+      if (f32) ((float *)ts_host.data())[t] = (float)ts64;
+      else ((double *)ts_host.data())[t] = ts64;
+    }
+    PA_TRY(cudaMemcpyAsync(d_ts_traj, ts_host.data(), tries * esz, cudaMemcpyHostToDevice, st));
+    auto run = [&](auto tag) -> cudaError_t {
+      using T = decltype(tag);
+      DenseParams<T> dp{};
+      dp.qoff = (const T *)p->d_qoff;
+      dp.diag = (const T *)p->d_diag;
+      dp.tscale = nullptr;
+      dp.ld = p->ld;
+      dp.n = p->n;
+      dp.num_iter = 1;
+      dp.sweeps_per_beta = prm->sweeps_per_step;
+      dp.mode = OSA_MODE_SEQUENTIAL_SWEEP;
+      dp.seed = prm->seed;
+      dp.first_try = first_try;
+      dp.num_tries = tries;
+      dp.best_rel = p->d_best_rel;
+      dp.best_states = p->d_states;
+      dp.nw = p->nw;
+      dp.counters = p->d_counters;
+      dp.init_states = d_cur;
+      dp.final_states = d_cur;
+      dp.tscale_traj = (const T *)d_ts_traj;
+      dp.step_base = (uint32_t)step * (uint32_t)prm->sweeps_per_step;
+      return launch_dense_seq_ws<T>(dp, st, &info);
+    };
+    PA_TRY(f32 ? run(float()) : run(double()));
+    PA_TRY(cudaStreamSynchronize(st));  // ts_host is rewritten by the next step
+    // best state of the step against the best kept so far in this slot (e_cur = start energy)
+    PA_TRY(launch_pt_track_best(d_ecur, p->d_best_rel, p->d_states, tries, p->nw, d_beste, d_keep, st));
+    launches += 2;
+    if (step + 1 == prm->num_steps) break;
+    rc = exact_energies(p, d_cur, tries, d_ecur);
+    if (rc) {
+      release();
+      return rc;
+    }
+    // weights for the move to the next temperature: exp(-(b' - b) E), b = inverse temperature
+    const double b0 = prm->accept_rule == OSA_ACCEPT_REFERENCE ? 1.0 / betas[step] : betas[step];
+    const double b1 =
+        prm->accept_rule == OSA_ACCEPT_REFERENCE ? 1.0 / betas[step + 1] : betas[step + 1];
+    PA_TRY(launch_pa_resample(prm->seed, prm->first_population, prm->num_populations, M,
+                              (uint32_t)step, -(b1 - b0), d_cur, d_ecur, p->nw, d_cum, d_nxt, d_enxt,
+                              nullptr, d_replaced, st));
+    std::swap(d_cur, d_nxt);
+    std::swap(d_ecur, d_enxt);
+    launches += 3;
+  }
+  PA_TRY(cudaEventRecord(p->ev[1], st));
+  rc = exact_energies(p, d_keep, tries, p->d_energy);
+  if (rc) {
+    release();
+    return rc;
+  }
+  ++launches;
+  PA_TRY(cudaEventRecord(p->ev[2], st));
+  PA_TRY(launch_argmin(p->d_energy, tries, p->d_arg_idx, p->d_arg_e, st));
+  ++launches;
+  PA_TRY(cudaEventRecord(p->ev[3], st));
+
+  unsigned long long h_idx = 0, h_replaced = 0;
+  double h_e = 0.0;
+  Counters h_cnt;
+  PA_TRY(cudaMemcpyAsync(&h_idx, p->d_arg_idx, sizeof(h_idx), cudaMemcpyDeviceToHost, st));
+  PA_TRY(cudaMemcpyAsync(&h_e, p->d_arg_e, sizeof(h_e), cudaMemcpyDeviceToHost, st));
+  PA_TRY(cudaMemcpyAsync(&h_cnt, p->d_counters, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+  PA_TRY(cudaMemcpyAsync(&h_replaced, d_replaced, sizeof(h_replaced), cudaMemcpyDeviceToHost, st));
+  {
+    cudaError_t sync_err = cudaStreamSynchronize(st);
+    if (sync_err != cudaSuccess) {
+      release();
+      return fail(OSA_ERR_CUDA, "population annealing kernels failed: %s", cudaGetErrorString(sync_err));
+    }
+  }
+  if (h_idx >= tries) {
+    release();
+    return fail(OSA_ERR_CUDA, "argmin returned an invalid index");
+  }
+  if (best_energies)
+    PA_TRY(cudaMemcpyAsync(best_energies, p->d_energy, tries * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (best_states_packed)
+    PA_TRY(cudaMemcpyAsync(best_states_packed, d_keep, words * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  std::vector<uint32_t> win(p->nw);
+  PA_TRY(cudaMemcpyAsync(win.data(), d_keep + (size_t)h_idx * p->nw, (size_t)p->nw * sizeof(uint32_t),
+                         cudaMemcpyDeviceToHost, st));
+  PA_TRY(cudaStreamSynchronize(st));
+  if (best_state)
+    for (int i = 0; i < p->n; ++i) best_state[i] = (uint8_t)((win[i >> 5] >> (i & 31)) & 1u);
+  if (best_energy) *best_energy = h_e;
+  if (best_index) *best_index = first_try + h_idx;
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->attempts = (uint64_t)prm->num_steps * (uint64_t)prm->sweeps_per_step * (uint64_t)p->n * tries;
+    stats->accepts = h_cnt.accepts;
+    stats->row_fetches = h_cnt.row_fetches;
+    stats->init_row_fetches = h_cnt.init_row_fetches;
+    stats->pt_swaps = h_replaced;
+    cudaEventElapsedTime(&ms_sweep, p->ev[0], p->ev[1]);
+    cudaEventElapsedTime(&ms_energy, p->ev[1], p->ev[2]);
+    stats->ms_sweep = ms_sweep;
+    stats->ms_energy = ms_energy;
+    cudaEventElapsedTime(&stats->ms_reduce, p->ev[2], p->ev[3]);
+    cudaEventElapsedTime(&stats->ms_total, p->ev[0], p->ev[3]);
+    stats->kernel_id = KID_DENSE_SEQ;
+    stats->traj_per_batch = info.traj_per_batch;
+    stats->q_elem_bytes = f32 ? 4 : 8;
+    stats->grid = info.grid;
+    stats->launches = launches;
+  }
+  release();
+#undef PA_TRY
+  return OSA_OK;
+}
+
 int osa_energy_batch(osa_problem *p, const uint32_t *states_packed, uint64_t count, double *out) {
   if (!p || !states_packed || !out) return fail(OSA_ERR_INVALID, "null argument");
   if (count == 0) return OSA_OK;

@@ -265,6 +265,12 @@ cudaError_t launch_pt_swap(uint64_t seed, uint64_t first_group, uint64_t num_gro
                            uint32_t round, const double *e_cur, const double *dinv,
                            const T *tscale_of_temp, int32_t *temp_of_slot, int32_t *slot_of_temp,
                            T *tscale_traj, unsigned long long *swap_count, cudaStream_t s);
+// population annealing (osa_pa.cu): integer weights + prefix sums, then the resampling copy
+cudaError_t launch_pa_resample(uint64_t seed, uint64_t first_pop, uint64_t num_pops, int M,
+                               uint32_t step, double neg_db, const uint32_t *cur,
+                               const double *e_cur, int nw, unsigned long long *cum, uint32_t *nxt,
+                               double *e_nxt, int32_t *src_out, unsigned long long *replaced,
+                               cudaStream_t s);
 bool dense_seq_supported(int n, int elem_bytes);
 bool dense_generic_supported(int n, int elem_bytes);
 size_t sparse_ws_words(int n, uint64_t num_tries);

@@ -253,7 +253,10 @@ __global__ void __launch_bounds__(WsRegs<DW>::THREADS, 1) k_dense_seq_ws(const D
     const int t = lane / NSEG, seg = lane % NSEG;
     const int r = dwarp + DW * t;
     const bool has = (t < TPW) && (r < R);
-    const int rr = has ? r : 0;
+    // lanes without a trajectory read along with the warp's own first trajectory (dwarp < DW <= R):
+    // their values are never used, but reading another warp's slot would be a (benign) race with
+    // that warp's writes -- compute-sanitizer racecheck flags it (profiles/r02/racecheck_*)
+    const int rr = has ? r : dwarp;
     const bool tv = has && r < nvalid;
     const bool lead = has && seg == 0;
     const int c0 = seg * HS;

@@ -43,6 +43,10 @@ def load():
     lib.orc_engine_draw.argtypes = [u64, u64, u32, u32, u32, vp]
     lib.orc_set_trace_output.argtypes = [vp]
     lib.orc_set_trace_output.restype = None
+    lib.orc_det_exp.argtypes = [ctypes.c_double]
+    lib.orc_det_exp.restype = ctypes.c_double
+    lib.orc_pa_resample.argtypes = [vp, ctypes.c_int, ctypes.c_double, u64, u64, u32, vp]
+    lib.orc_pa_resample.restype = None
     lib.orc_neglogf.argtypes = [u32]
     lib.orc_neglogf.restype = ctypes.c_float
     lib.orc_init_bit.argtypes = [u64, u64, u32]
@@ -83,6 +87,19 @@ def philox(ctr, key):
 
 def neglogf(w):
     return float(load().orc_neglogf(int(w)))
+
+
+def det_exp(x):
+    return load().orc_det_exp(float(x))
+
+
+def pa_resample(energies, neg_db, seed, population, step):
+    """Source replica of every slot after one resampling step of osa_pa_anneal."""
+    e = np.ascontiguousarray(energies, dtype=np.float64)
+    src = np.zeros(e.shape[0], dtype=np.int32)
+    load().orc_pa_resample(e.ctypes.data, e.shape[0], float(neg_db), seed, population, step,
+                           src.ctypes.data)
+    return src
 
 
 def ref_energy(flat_qubo, state):

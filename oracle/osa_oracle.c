@@ -541,3 +541,60 @@ DEFINE_REPLAY_DENSE(orc_replay_dense_f64, double, fma)
 
 DEFINE_REPLAY_CSR(orc_replay_csr_f32, float)
 DEFINE_REPLAY_CSR(orc_replay_csr_f64, double)
+
+/* ------------------------------------------------------------------------- */
+/* (C) population annealing: the resampling step of osa_pa_anneal            */
+/* ------------------------------------------------------------------------- */
+
+/* exp(x) for x <= 0, the fixed operation sequence of the engine (onesolver_b200/csrc/osa_pa.cu,
+ * det_exp): k = rint(x log2 e), two-part ln 2 reduction, degree-13 Taylor polynomial in Horner
+ * form with fma, exact scaling by 2^k.  Written from the definition in the C ABI header; every
+ * operation is correctly rounded, so host and device agree bit for bit.                        */
+double orc_det_exp(double x) {
+  if (!(x >= -60.0)) return 0.0;
+  const double kf = rint(x * 1.4426950408889634074);
+  double r = fma(-kf, 6.93147180369123816490e-01, x);
+  r = fma(-kf, 1.90821492927058770002e-10, r);
+  static const double c[12] = {2.08767569878681e-09,   2.505210838544172e-08, 2.755731922398589e-07,
+                               2.7557319223985893e-06, 2.48015873015873e-05,  1.984126984126984e-04,
+                               1.388888888888889e-03,  8.333333333333333e-03, 4.1666666666666664e-02,
+                               1.6666666666666666e-01, 0.5,                   1.0};
+  double p = 1.6059043836821613e-10;
+  for (int i = 0; i < 12; ++i) p = fma(p, r, c[i]);
+  p = fma(p, r, 1.0);
+  const int64_t k = (int64_t)kf;
+  union { uint64_t u; double d; } scale;
+  scale.u = (uint64_t)(1023 + k) << 52;
+  return p * scale.d;
+}
+
+/* One population, one resampling step (include/onesolver_b200.h, osa_pa_anneal):
+ *   x_i = neg_db * E_i, q_i = floor(2^40 exp(x_i - max x)), C = prefix sums of q, W = C[M-1],
+ *   r = floor(W u32 / 2^32), slot j continues from src[j] = min{ i : C_i > floor((j W + r) / M) }.
+ * u32 = word 0 of the Philox draw (stream 3, c0 = 0x50410000, c1 = step, id = population).     */
+void orc_pa_resample(const double *e, int m, double neg_db, uint64_t seed, uint64_t population,
+                     uint32_t step, int32_t *src) {
+  double mx = -INFINITY;
+  for (int i = 0; i < m; ++i) {
+    const double x = neg_db * e[i];
+    if (x > mx) mx = x;
+  }
+  uint64_t *cum = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)m);
+  uint64_t run = 0;
+  for (int i = 0; i < m; ++i) {
+    const double w = orc_det_exp(neg_db * e[i] + (-mx));
+    run += (uint64_t)(w * 1099511627776.0);
+    cum[i] = run;
+  }
+  uint32_t d[4];
+  orc_engine_draw(seed, population, 3u, 0x50410000u, step, d);
+  const unsigned __int128 W = run;
+  const uint64_t r = (uint64_t)((W * d[0]) >> 32);
+  int i = 0;
+  for (int j = 0; j < m; ++j) {
+    const uint64_t pos = (uint64_t)(((unsigned __int128)j * W + r) / (unsigned __int128)m);
+    while (cum[i] <= pos) ++i; /* pos < W = cum[m-1], so i stays in range; pos grows with j */
+    src[j] = i;
+  }
+  free(cum);
+}

@@ -161,6 +161,12 @@ void orc_energy_packed(const double *qsym, int n, const uint32_t *states_packed,
 
 int orc_num_threads(void);
 
+/* (C) population annealing: deterministic exp and one resampling step of osa_pa_anneal
+ * (include/onesolver_b200.h); src[m] receives the source replica of every slot.            */
+double orc_det_exp(double x);
+void orc_pa_resample(const double *e, int m, double neg_db, uint64_t seed, uint64_t population,
+                     uint32_t step, int32_t *src);
+
 #ifdef __cplusplus
 }
 #endif

@@ -400,7 +400,15 @@ def test_single_role_kernel_is_bit_identical_to_warp_specialised(gpu, monkeypatc
     scale = np.sqrt(n)
     sched = geo(3, 0.02 * scale, 0.6 * scale)
     a, _ = run_and_compare_dense(q, sched, 3, tries, capi.MODE_SEQUENTIAL_SWEEP, dtype)
+    # the other warp-specialised variant (lock-step roles <-> free-running roles): the default
+    # picks the free-running kernel for N = 4096 fp32 only (osa_dense_seq.cu, use_flow)
+    monkeypatch.setenv("OSA_WS_FLOW", "0" if (n == 4096 and dtype == np.float32) else "1")
+    c, _ = run_and_compare_dense(q, sched, 3, tries, capi.MODE_SEQUENTIAL_SWEEP, dtype)
+    monkeypatch.delenv("OSA_WS_FLOW")
     monkeypatch.setenv("OSA_DS_WS", "0")
     b, _ = run_and_compare_dense(q, sched, 3, tries, capi.MODE_SEQUENTIAL_SWEEP, dtype)
     np.testing.assert_array_equal(a.best_states_packed, b.best_states_packed)
+    np.testing.assert_array_equal(a.best_states_packed, c.best_states_packed)
+    np.testing.assert_array_equal(a.trace_hash, b.trace_hash)
+    np.testing.assert_array_equal(a.trace_hash, c.trace_hash)
     assert a.stats["grid"] != 0 and b.stats["grid"] != 0
