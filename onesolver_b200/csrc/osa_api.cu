@@ -360,8 +360,10 @@ int osa_problem_create_csr_f64(const int32_t *rowptr, const int32_t *col, const 
   if (rowptr[0] != 0) return fail(OSA_ERR_INVALID, "rowptr[0] must be 0");
   const int64_t nnz = rowptr[n];
   if (nnz < 0 || (nnz > 0 && (!col || !val))) return fail(OSA_ERR_INVALID, "bad CSR arrays");
-  if ((size_t)n * sizeof(uint32_t) > 227 * 1024)
-    return fail(OSA_ERR_UNSUPPORTED, "sparse kernel supports n <= %d", 227 * 1024 / 4);
+  if (!sparse_supported(n, sweep_precision == OSA_SWEEP_F32 ? 4 : 8))
+    return fail(OSA_ERR_UNSUPPORTED,
+                "sparse kernel supports n <= about %d (spin words of 32 trajectories in shared memory)",
+                (227 * 1024 - 8192) / 4);
   for (int i = 0; i < n; ++i) {
     if (rowptr[i + 1] < rowptr[i]) return fail(OSA_ERR_INVALID, "rowptr not monotone at %d", i);
     for (int32_t q = rowptr[i]; q < rowptr[i + 1]; ++q) {
@@ -413,24 +415,64 @@ int osa_problem_create_csr_f64(const int32_t *rowptr, const int32_t *col, const 
   step(dev_alloc(&p->d_val64, nnz_a * sizeof(double), p->stream));
   step(dev_alloc(&p->d_diag64, (size_t)n * sizeof(double), p->stream));
   step(dev_alloc(&p->d_val, (nnz_a + (size_t)n) * esz, p->stream));
-  // groups of four consecutive sites (32b + 4g ..) without a coupling among them: the sparse sweep
-  // gathers their fields side by side (k_sparse)
-  const int nblk32 = (n + 31) / 32;
-  std::vector<uint32_t> indep((size_t)nblk32, 0u);
-  for (int i0 = 0; i0 + 4 <= n; i0 += 4) {
-    bool free = true;
-    for (int a = i0; a < i0 + 4 && free; ++a)
+  // grouped layout of the sequential sweeps (osa_sparse.cu): groups of four consecutive sites,
+  // entry (t, k) = t-th neighbour of site 4g + k as {byte offset of its spin word, coupling in the
+  // sweep precision}, short rows padded with {offset of the zero word n, 0}; a group is flagged
+  // independent when no coupling joins two of its four sites
+  const int nblk32 = (n + 31) / 32, ngroups = nblk32 * 8;
+  std::vector<uint32_t> gbase((size_t)ngroups + 1), ginfo((size_t)ngroups), ent_off;
+  std::vector<double> ent_val;
+  ent_off.reserve((size_t)nnz + (size_t)n);
+  ent_val.reserve((size_t)nnz + (size_t)n);
+  for (int g = 0; g < ngroups; ++g) {
+    const int i0 = g * 4;
+    gbase[(size_t)g] = (uint32_t)ent_off.size();
+    int len = 0;
+    bool indep = i0 + 4 <= n;
+    for (int a = i0; a < i0 + 4 && a < n; ++a) {
+      len = std::max(len, (int)(rowptr[a + 1] - rowptr[a]));
       for (int32_t q = rowptr[a]; q < rowptr[a + 1]; ++q)
-        if (col[q] >= i0 && col[q] < i0 + 4) {
-          free = false;
-          break;
-        }
-    if (free) indep[(size_t)(i0 >> 5)] |= 1u << ((i0 & 31) >> 2);
+        if (col[q] >= i0 && col[q] < i0 + 4) indep = false;
+    }
+    if (len > 0xffff) {
+      osa_problem_destroy(p);
+      return fail(OSA_ERR_UNSUPPORTED, "sparse kernel supports at most 65535 neighbours per site");
+    }
+    for (int t = 0; t < len; ++t)
+      for (int k = 0; k < 4; ++k) {
+        const int a = i0 + k;
+        const bool real = a < n && t < rowptr[a + 1] - rowptr[a];
+        ent_off.push_back(real ? (uint32_t)col[rowptr[a] + t] * 4u : (uint32_t)n * 4u);
+        ent_val.push_back(real ? val[rowptr[a] + t] : 0.0);
+      }
+    ginfo[(size_t)g] = (uint32_t)len | (indep ? 0x10000u : 0u);
   }
-  step(dev_alloc(&p->d_indep, (size_t)nblk32 * sizeof(uint32_t), p->stream));
+  gbase[(size_t)ngroups] = (uint32_t)ent_off.size();
+  p->stage_ok = 1;
+  for (int h = 0; h < nblk32 * 2; ++h)
+    if (gbase[(size_t)h * 4 + 4] - gbase[(size_t)h * 4] > (uint32_t)SPARSE_HALF_CAP) p->stage_ok = 0;
+  const size_t nent = ent_off.size(), nent_a = nent > 0 ? nent : 1;
+  const size_t ent_bytes = sweep_precision == OSA_SWEEP_F32 ? 8 : 16;
+  std::vector<unsigned char> ent(nent_a * ent_bytes, 0);
+  for (size_t q = 0; q < nent; ++q) {
+    unsigned char *dst = ent.data() + q * ent_bytes;
+    memcpy(dst, &ent_off[q], 4);
+    if (sweep_precision == OSA_SWEEP_F32) {
+      const float v = (float)ent_val[q];  // round to nearest, like k_convert
+      memcpy(dst + 4, &v, 4);
+    } else {
+      memcpy(dst + 8, &ent_val[q], 8);
+    }
+  }
+  step(dev_alloc(&p->d_gbase, ((size_t)ngroups + 1) * sizeof(uint32_t), p->stream));
+  step(dev_alloc(&p->d_ginfo, (size_t)ngroups * sizeof(uint32_t), p->stream));
+  step(dev_alloc(&p->d_gent, ent.size(), p->stream));
   if (e == cudaSuccess) {
-    step(cudaMemcpyAsync(p->d_indep, indep.data(), (size_t)nblk32 * sizeof(uint32_t),
+    step(cudaMemcpyAsync(p->d_gbase, gbase.data(), gbase.size() * sizeof(uint32_t),
                          cudaMemcpyHostToDevice, p->stream));
+    step(cudaMemcpyAsync(p->d_ginfo, ginfo.data(), ginfo.size() * sizeof(uint32_t),
+                         cudaMemcpyHostToDevice, p->stream));
+    step(cudaMemcpyAsync(p->d_gent, ent.data(), ent.size(), cudaMemcpyHostToDevice, p->stream));
     step(cudaMemcpyAsync(p->d_rowptr, rowptr, (size_t)(n + 1) * sizeof(int32_t),
                          cudaMemcpyHostToDevice, p->stream));
     if (nnz > 0) {
@@ -474,7 +516,9 @@ int osa_problem_destroy(osa_problem *p) {
     dev_free(p->d_val, st);
     dev_free(p->d_val64, st);
     dev_free(p->d_diag64, st);
-    dev_free(p->d_indep, st);
+    dev_free(p->d_gbase, st);
+    dev_free(p->d_ginfo, st);
+    dev_free(p->d_gent, st);
   } else {
     dev_free(p->d_qoff, st);
     dev_free(p->d_diag, st);
@@ -612,7 +656,10 @@ int osa_anneal_traced(osa_problem *p, const double *beta_schedule, const osa_ann
       sp.nw = p->nw;
       sp.counters = p->d_counters;
       sp.trace_hash = trace_hash ? p->d_trace : nullptr;
-      sp.indep = p->d_indep;
+      sp.gbase = p->d_gbase;
+      sp.ginfo = p->d_ginfo;
+      sp.gent = p->d_gent;
+      sp.stage_ok = p->stage_ok;
       return launch_sparse<T>(sp, p->stream, &info);
     };
     CUDA_TRY(f32 ? run(float()) : run(double()));

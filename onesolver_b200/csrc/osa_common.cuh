@@ -215,8 +215,11 @@ struct SparseParams {
   int nw;
   Counters *counters;
   unsigned long long *trace_hash;  // optional [num_tries], see trace_step()
-  // optional [ceil(n/32)]: bit g of word b = sites 32b+4g .. 32b+4g+3 are pairwise non-adjacent
-  const uint32_t *indep;
+  // grouped layout of the sequential sweeps (osa_sparse.cu): groups of four consecutive sites
+  const uint32_t *gbase;  // [8 * ceil(n/32) + 1] first entry of a group
+  const uint32_t *ginfo;  // [8 * ceil(n/32)] len | independent << 16
+  const void *gent;       // SpEnt<T>[gbase[last]]: entry (t, k) of group g at gbase[g] + 4 t + k
+  int stage_ok;           // every half block (4 groups) fits the staging buffer
 };
 
 // Timing-experiment switches that make the results of a call meaningless (skipped row streaming,
@@ -274,6 +277,8 @@ cudaError_t launch_pa_resample(uint64_t seed, uint64_t first_pop, uint64_t num_p
 bool dense_seq_supported(int n, int elem_bytes);
 bool dense_generic_supported(int n, int elem_bytes);
 size_t sparse_ws_words(int n, uint64_t num_tries);
+bool sparse_supported(int n, int elem_bytes);
+constexpr int SPARSE_HALF_CAP = 256;  // = SP_HALF_CAP of osa_sparse.cu
 
 // exact fp64 energies (reference formula) of packed states
 cudaError_t launch_energy_dense(const double *q64, size_t ld64, int n, const uint32_t *states,

@@ -26,7 +26,10 @@ struct osa_problem {
   void *d_val = nullptr;      // sweep precision
   double *d_val64 = nullptr;
   double *d_diag64 = nullptr;
-  uint32_t *d_indep = nullptr;  // [ceil(n/32)] groups of four pairwise non-adjacent sites (k_sparse)
+  // grouped layout of the sequential sparse sweep (osa_sparse.cu): groups of four sites
+  uint32_t *d_gbase = nullptr, *d_ginfo = nullptr;
+  unsigned char *d_gent = nullptr;
+  int stage_ok = 0;
   // execution
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};

@@ -25,25 +25,42 @@ namespace osa {
 
 namespace {
 
-// CSR entries of one block of 32 consecutive sites, staged per warp in shared memory
-constexpr int SP_LOG = 64;   // flips remembered per trajectory after leaving a best state
-constexpr int SP_CAP = 512;  // entries per staging buffer (32 sites x degree 16); larger blocks
-                             // fall back to direct global loads
+// Sequential sweeps read the couplings from a GROUPED layout built at problem creation
+// (osa_api.cu, build_sparse_groups): the sites are taken in groups of four consecutive ones; a
+// group stores len x 4 entries, entry (t, k) = the t-th neighbour of site 4g + k as
+// {byte offset of its spin word in X, coupling}, rows shorter than the longest of the four padded
+// with {offset of an always-zero word, 0}.  A pad never adds anything (its spin bit is 0), so the
+// additions of a row stay the CSR ones in CSR order.  One 16-byte shared-memory load brings two
+// (fp32) entries, the spin word address needs no arithmetic, and for groups whose four sites are
+// pairwise non-adjacent (flagged at creation) the four fields are independent chains that run
+// side by side: about 4 instructions per neighbour instead of 12 for the plain CSR walk.
+constexpr int SP_LOG = 64;        // flips remembered per trajectory after leaving a best state
+constexpr int SP_HALF_CAP = 256;  // entries per staging buffer: half a block = 16 sites x degree 16
 
-template <typename T>
-struct SpStage {
-  int32_t col[2][SP_CAP];
-  T val[2][SP_CAP];
+template <typename T> struct SpEnt;
+template <> struct __align__(8) SpEnt<float> {
+  uint32_t xoff;
+  float val;
+};
+template <> struct __align__(16) SpEnt<double> {
+  uint32_t xoff, pad;
+  double val;
 };
 
 __device__ __forceinline__ uint32_t sp_smem_addr(const void *p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
 
-template <typename T>
+// ONE_WARP: the CTA is a single warp, so every shared-memory base address is CTA-uniform (the spin
+// word of a neighbour is then one load at [offset register + uniform base]); used whenever shared
+// memory, not the 32-CTA limit, bounds the residency.  STAGED: the entries of the next half block
+// are copied into shared memory with cp.async while the current one is processed.
+template <typename T, bool ONE_WARP, bool STAGED>
 __global__ void k_sparse(const SparseParams<T> p, int x_words_per_warp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  using Ent = SpEnt<T>;
+  const int lane = threadIdx.x & 31;
+  const int warp = ONE_WARP ? 0 : (int)(threadIdx.x >> 5), wpb = ONE_WARP ? 1 : (int)(blockDim.x >> 5);
   const uint64_t gw = (uint64_t)blockIdx.x * wpb + warp;
   const uint64_t tl0 = gw * 32ull;
   if (tl0 >= p.num_tries) return;  // whole warp leaves; no block-level barrier below
@@ -52,11 +69,15 @@ __global__ void k_sparse(const SparseParams<T> p, int x_words_per_warp) {
   const uint64_t traj = p.first_try + tl;
   const int n = p.n;
 
-  // shared memory: [wpb] staging structs, then [wpb][x_words_per_warp] spin words
-  SpStage<T> *stage = reinterpret_cast<SpStage<T> *>(smem_raw) + warp;
-  uint32_t *X = reinterpret_cast<uint32_t *>(smem_raw + (size_t)wpb * sizeof(SpStage<T>)) +
-                (size_t)warp * x_words_per_warp;
+  // shared memory per warp: [2][SP_HALF_CAP] staged entries, then x_words_per_warp spin words
+  // (>= n + 1: the words from n on stay zero, the pads of the grouped layout point at word n)
+  constexpr size_t STAGE_BYTES = 2 * SP_HALF_CAP * sizeof(Ent);
+  const size_t per_warp = STAGE_BYTES + (size_t)x_words_per_warp * sizeof(uint32_t);
+  unsigned char *mine = smem_raw + (size_t)warp * per_warp;
+  Ent *stage = reinterpret_cast<Ent *>(mine);
+  uint32_t *X = reinterpret_cast<uint32_t *>(mine + STAGE_BYTES);
   uint32_t *XB = p.xbest_ws + gw * (uint64_t)n;
+  for (int j = n + lane; j < x_words_per_warp; j += 32) X[j] = 0u;
 
   // initial spins: lane draws its own packed word, the warp transposes it with ballots
   for (int j0 = 0; j0 < n; j0 += 32) {
@@ -124,70 +145,80 @@ __global__ void k_sparse(const SparseParams<T> p, int x_words_per_warp) {
   };
 
   if (p.mode == OSA_MODE_SEQUENTIAL_SWEEP) {
-    // The CSR arrays (~10 bytes per neighbour) live in L2; reading them with dependent loads
-    // would put 2-3 L2 round trips on every site.  Instead the entries of the NEXT block of 32
-    // sites are copied into a per-warp shared-memory buffer with cp.async while the current
-    // block is processed (double buffer), and rowptr/diag of the next block are prefetched into
-    // registers, so the per-site critical path only touches shared memory.
+    // Blocks of 32 sites (one Philox block per 4 sites, one trace update per block), staged in
+    // halves of 16 sites = 4 groups.  Lane l <= 8 holds the entry base of group l of the block
+    // (lane 8: its end), lane l < 8 the group's {len, independent}, lane l the diagonal of site l;
+    // the same for the next block is loaded one block ahead.
     const int nblk = (n + 31) >> 5;
-    auto block_range = [&](int b, int &e0, int &e1) {
-      e0 = __ldg(p.rowptr + b * 32);
-      e1 = __ldg(p.rowptr + min(b * 32 + 32, n));
+    const uint32_t lanebit = 1u << lane;
+    const Ent *gent = reinterpret_cast<const Ent *>(p.gent);
+    auto load_meta = [&](int b, uint32_t &gb, uint32_t &gi, T &dg) {
+      gb = __ldg(p.gbase + b * 8 + min(lane, 8));
+      gi = lane < 8 ? __ldg(p.ginfo + b * 8 + lane) : 0u;
+      const int i = b * 32 + lane;
+      dg = (i < n) ? __ldg(p.diag + i) : (T)0;
     };
-    auto prefetch_entries = [&](int b, int buf) {  // always commits one group
-      int e0, e1;
-      block_range(b, e0, e1);
-      if (e1 - e0 <= SP_CAP) {
-        for (int q = e0 + lane; q < e1; q += 32) {
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(
-                           sp_smem_addr(&stage->col[buf][q - e0])),
-                       "l"(p.col + q)
-                       : "memory");
+    auto prefetch = [&](uint32_t s0, uint32_t s1, int buf) {  // always commits one group
+      if (STAGED) {
+        for (uint32_t q = s0 + lane; q < s1; q += 32)
           asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(
-                           sp_smem_addr(&stage->val[buf][q - e0])),
-                       "l"(p.val + q), "n"((int)sizeof(T))
+                           sp_smem_addr(stage + buf * SP_HALF_CAP + (q - s0))),
+                       "l"(gent + q), "n"((int)sizeof(Ent))
                        : "memory");
-        }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto load_meta = [&](int b, int &rp_lo, int &rp_hi, T &dg) {
-      const int i = b * 32 + lane;
-      rp_lo = __ldg(p.rowptr + min(i, n));
-      rp_hi = __ldg(p.rowptr + min(i + 1, n));
-      dg = (i < n) ? __ldg(p.diag + i) : (T)0;
+    // spin word of a neighbour: X + byte offset
+    auto xword = [&](uint32_t off) {
+      return *reinterpret_cast<const uint32_t *>(reinterpret_cast<const unsigned char *>(X) + off);
+    };
+    // four consecutive entries (t, 0..3) / one entry, from the staging buffer or from global memory
+    auto load4 = [&](const Ent *e, Ent (&o)[4]) {
+      if constexpr (sizeof(T) == 4) {
+        const uint4 a = STAGED ? *reinterpret_cast<const uint4 *>(e) : __ldg(reinterpret_cast<const uint4 *>(e));
+        const uint4 c = STAGED ? *reinterpret_cast<const uint4 *>(e + 2) : __ldg(reinterpret_cast<const uint4 *>(e + 2));
+        o[0].xoff = a.x; o[0].val = __uint_as_float(a.y);
+        o[1].xoff = a.z; o[1].val = __uint_as_float(a.w);
+        o[2].xoff = c.x; o[2].val = __uint_as_float(c.y);
+        o[3].xoff = c.z; o[3].val = __uint_as_float(c.w);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint4 a = STAGED ? *reinterpret_cast<const uint4 *>(e + k) : __ldg(reinterpret_cast<const uint4 *>(e + k));
+          o[k].xoff = a.x;
+          o[k].val = __hiloint2double((int)a.w, (int)a.z);
+        }
+      }
+    };
+    auto load1 = [&](const Ent *e, Ent &o) {
+      if constexpr (sizeof(T) == 4) {
+        const uint2 a = STAGED ? *reinterpret_cast<const uint2 *>(e) : __ldg(reinterpret_cast<const uint2 *>(e));
+        o.xoff = a.x; o.val = __uint_as_float(a.y);
+      } else {
+        const uint4 a = STAGED ? *reinterpret_cast<const uint4 *>(e) : __ldg(reinterpret_cast<const uint4 *>(e));
+        o.xoff = a.x;
+        o.val = __hiloint2double((int)a.w, (int)a.z);
+      }
     };
 
-    int rp_lo, rp_hi, nrp_lo, nrp_hi;
+    uint32_t gb, gi, ngb, ngi;
     T dg, ndg;
-    prefetch_entries(0, 0);
-    load_meta(0, rp_lo, rp_hi, dg);
-    long long gblock = 0;
+    load_meta(0, gb, gi, dg);
+    prefetch(__shfl_sync(0xffffffffu, gb, 0), __shfl_sync(0xffffffffu, gb, 4), 0);
+    unsigned hcount = 0;
     uint32_t step = 0;
     for (int iter = 0; iter < p.num_iter; ++iter) {
       const T ts = p.tscale[iter];
       for (int sw = 0; sw < p.sweeps_per_beta; ++sw, ++step) {
-        U4 d = U4{0, 0, 0, 0};
-        for (int b = 0; b < nblk; ++b, ++gblock) {
-          const int buf = (int)(gblock & 1);
+        for (int b = 0; b < nblk; ++b) {
           const int bn = (b + 1 == nblk) ? 0 : b + 1;  // next block (wraps into the next sweep)
-          prefetch_entries(bn, buf ^ 1);
-          load_meta(bn, nrp_lo, nrp_hi, ndg);
-          asm volatile("cp.async.wait_group 1;" ::: "memory");  // this block's entries landed
-          __syncwarp();
-          const int e0 = __shfl_sync(0xffffffffu, rp_lo, 0);
-          const int e1 = __shfl_sync(0xffffffffu, rp_hi, min(31, n - b * 32 - 1));
-          const bool staged = (e1 - e0) <= SP_CAP;
+          load_meta(bn, ngb, ngi, ndg);
           const int i_end = min(32, n - b * 32);
-          // one Philox block serves four consecutive sites: their four thresholds (a chain of
-          // ~40 dependent operations each) are computed together so the chains overlap, and sit
-          // off the critical path of three of the four site steps
           uint32_t blk_acc = 0u;  // sites of this block that this lane's trajectory flipped
-          const uint32_t indep = p.indep ? __ldg(p.indep + b) : 0u;
           // decision of site i (field hk in hand): accept test, bookkeeping, spin update
           auto decide = [&](int s, int i, T hk, T theta) {
             const uint32_t xiw = X[i];
-            const T dE = ((xiw >> lane) & 1u) ? -hk : hk;
+            const T dE = (xiw & lanebit) ? -hk : hk;
             const bool acc = tv && (dE < theta);
             const bool overflow = acc ? track(i, dE) : false;
             const uint32_t spill = __ballot_sync(0xffffffffu, overflow);
@@ -203,72 +234,68 @@ __global__ void k_sparse(const SparseParams<T> p, int x_words_per_warp) {
               __syncwarp();
             }
           };
-          for (int s4 = 0; s4 < i_end; s4 += 4) {
-            d = engine_draw(p.seed, traj, STREAM_SEQ, (uint32_t)(b * 32 + s4) >> 2, step);
-            const T th4[4] = {threshold<T>(ts, d.x), threshold<T>(ts, d.y), threshold<T>(ts, d.z),
-                              threshold<T>(ts, d.w)};
-            if (staged && e1 > e0 && s4 + 4 <= i_end && ((indep >> (s4 >> 2)) & 1u)) {
-              // The four sites are pairwise non-adjacent (precomputed per block at problem
-              // creation), so none of their flips changes the field of another: the four
-              // neighbour gathers are independent chains and run side by side, the decisions
-              // follow in site order.  Rows are padded to the longest of the four with +0.0
-              // (h + 0 = h), the additions of a row stay in CSR order -- the same bits as the
-              // one-site-at-a-time path below.
-              const int32_t *sc = stage->col[buf] - e0;
-              const T *sv = stage->val[buf] - e0;
-              int pb[4], pe[4];
-              T hk[4];
-              int len = 0;
+#pragma unroll 1
+          for (int hh = 0; hh < 2; ++hh) {
+            const int buf = (int)(hcount & 1u);
+            ++hcount;
+            // entries of the half after this one: second half of this block / first of the next
+            const uint32_t n0 = hh == 0 ? __shfl_sync(0xffffffffu, gb, 4) : __shfl_sync(0xffffffffu, ngb, 0);
+            const uint32_t n1 = hh == 0 ? __shfl_sync(0xffffffffu, gb, 8) : __shfl_sync(0xffffffffu, ngb, 4);
+            prefetch(n0, n1, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");  // this half's entries landed
+            __syncwarp();
+            const uint32_t h0 = __shfl_sync(0xffffffffu, gb, hh * 4);
+#pragma unroll 1
+            for (int g = hh * 4; g < hh * 4 + 4; ++g) {
+              const int s4 = g * 4;
+              if (s4 >= i_end) break;
+              // one Philox block serves the four sites of the group: their four thresholds (a
+              // chain of ~40 dependent operations each) are computed together so the chains overlap
+              const U4 d = engine_draw(p.seed, traj, STREAM_SEQ, (uint32_t)(b * 32 + s4) >> 2, step);
+              const T th4[4] = {threshold<T>(ts, d.x), threshold<T>(ts, d.y), threshold<T>(ts, d.z),
+                                threshold<T>(ts, d.w)};
+              const uint32_t base = __shfl_sync(0xffffffffu, gb, g);
+              const uint32_t info = __shfl_sync(0xffffffffu, gi, g);
+              const int len = (int)(info & 0xffffu);
+              const Ent *e = STAGED ? stage + buf * SP_HALF_CAP + (base - h0) : gent + base;
+              if (info & 0x10000u) {
+                // pairwise non-adjacent sites: none of their flips changes the field of another,
+                // so the four gathers run side by side and the decisions follow in site order
+                T hk[4];
 #pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4) {
-                pb[k4] = __shfl_sync(0xffffffffu, rp_lo, s4 + k4);
-                pe[k4] = __shfl_sync(0xffffffffu, rp_hi, s4 + k4);
-                hk[k4] = __shfl_sync(0xffffffffu, dg, s4 + k4);
-                len = max(len, pe[k4] - pb[k4]);
-              }
-              for (int t = 0; t < len; ++t) {
+                for (int k4 = 0; k4 < 4; ++k4) hk[k4] = __shfl_sync(0xffffffffu, dg, s4 + k4);
+#pragma unroll 2
+                for (int t = 0; t < len; ++t) {
+                  Ent en[4];
+                  load4(e + t * 4, en);
+#pragma unroll
+                  for (int k4 = 0; k4 < 4; ++k4)
+                    if (xword(en[k4].xoff) & lanebit) hk[k4] = det::add(hk[k4], en[k4].val);
+                }
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) decide(s4 + k4, b * 32 + s4 + k4, hk[k4], th4[k4]);
+              } else {
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4) {
-                  const int q = pb[k4] + t;
-                  const int qc = min(q, e1 - 1);
-                  const T v = q < pe[k4] ? sv[qc] : (T)0;
-                  if ((X[sc[qc]] >> lane) & 1u) hk[k4] = det::add(hk[k4], v);
+                  const int s = s4 + k4;
+                  if (s >= i_end) break;
+                  T hk = __shfl_sync(0xffffffffu, dg, s);
+#pragma unroll 4
+                  for (int t = 0; t < len; ++t) {
+                    Ent en;
+                    load1(e + t * 4 + k4, en);
+                    if (xword(en.xoff) & lanebit) hk = det::add(hk, en.val);
+                  }
+                  decide(s, b * 32 + s, hk, th4[k4]);
                 }
               }
-#pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4) decide(s4 + k4, b * 32 + s4 + k4, hk[k4], th4[k4]);
-              continue;
             }
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-              const int s = s4 + k4;
-              if (s >= i_end) break;
-              const int i = b * 32 + s;
-              const int pb = __shfl_sync(0xffffffffu, rp_lo, s);
-              const int pe = __shfl_sync(0xffffffffu, rp_hi, s);
-              T hk = __shfl_sync(0xffffffffu, dg, s);
-              if (staged) {
-                const int32_t *sc = stage->col[buf] - e0;
-                const T *sv = stage->val[buf] - e0;
-  #pragma unroll 4
-                for (int q = pb; q < pe; ++q) {
-                  if ((X[sc[q]] >> lane) & 1u) hk = det::add(hk, sv[q]);
-                }
-              } else {
-                for (int q = pb; q < pe; ++q) {
-                  const int c = __ldg(p.col + q);
-                  const T v = __ldg(p.val + q);
-                  if ((X[c] >> lane) & 1u) hk = det::add(hk, v);
-                }
-              }
-              decide(s, i, hk, th4[k4]);
-            }
+            __syncwarp();  // everyone is done with stage buffer `buf` before it is refilled
           }
           if (blk_acc != 0u) trace = trace_step(trace, step, (uint32_t)b, blk_acc);
-          rp_lo = nrp_lo;
-          rp_hi = nrp_hi;
+          gb = ngb;
+          gi = ngi;
           dg = ndg;
-          __syncwarp();  // everyone is done with stage buffer `buf` before it is refilled
         }
       }
     }
@@ -335,9 +362,11 @@ __global__ void k_sparse(const SparseParams<T> p, int x_words_per_warp) {
 
 constexpr size_t kMaxSmem = 227 * 1024;
 
+int sp_x_words(int n) { return (n + 1 + 3) / 4 * 4; }  // >= n + 1: word n is the always-zero pad word
+
 template <typename T>
 size_t sp_per_warp_bytes(int n) {
-  return sizeof(SpStage<T>) + (size_t)((n + 3) / 4 * 4) * sizeof(uint32_t);
+  return 2 * SP_HALF_CAP * sizeof(SpEnt<T>) + (size_t)sp_x_words(n) * sizeof(uint32_t);
 }
 
 int pick_wpb(size_t per_warp, uint64_t num_tries, int sm_count) {
@@ -357,36 +386,59 @@ int pick_wpb(size_t per_warp, uint64_t num_tries, int sm_count) {
   return wpb;
 }
 
+template <typename T, bool ONE_WARP, bool STAGED>
+cudaError_t launch_one(const SparseParams<T> &pp, int wpb, size_t smem, unsigned grid, int x_words,
+                       cudaStream_t s) {
+  cudaError_t err = cudaFuncSetAttribute(k_sparse<T, ONE_WARP, STAGED>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  k_sparse<T, ONE_WARP, STAGED><<<grid, wpb * 32, smem, s>>>(pp, x_words);
+  return cudaGetLastError();
+}
+
 template <typename T>
 cudaError_t launch_impl(const SparseParams<T> &p, cudaStream_t s, LaunchInfo *info) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const size_t per_warp = sp_per_warp_bytes<T>(p.n);
+  if (per_warp > kMaxSmem) return cudaErrorInvalidValue;
   SparseParams<T> pp = p;
   pp.log_base = (size_t)((p.num_tries + 31) / 32) * (size_t)p.n;  // words; see sparse_ws_words
   pp.debug_flags = probe_env_int("OSA_SP_DEBUG");  // timing experiments (probe builds only)
-  const int wpb = pick_wpb(per_warp, p.num_tries, sms);
+  // one-warp CTAs while shared memory (not the limit of 32 resident CTAs) bounds the residency
+  const bool one_warp = per_warp * 32 >= kMaxSmem;
+  const int wpb = one_warp ? 1 : pick_wpb(per_warp, p.num_tries, sms);
   if (wpb < 1) return cudaErrorInvalidValue;
   const size_t smem = (size_t)wpb * per_warp;
-  const int x_words = (p.n + 3) / 4 * 4;
-  cudaError_t err =
-      cudaFuncSetAttribute(k_sparse<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (err != cudaSuccess) return err;
+  const int x_words = sp_x_words(p.n);
   const uint64_t warps = (p.num_tries + 31) / 32;
   const uint64_t grid64 = (warps + wpb - 1) / wpb;
   if (grid64 == 0 || grid64 > 0x7fffffffull) return cudaErrorInvalidValue;
-  k_sparse<T><<<(unsigned)grid64, wpb * 32, smem, s>>>(pp, x_words);
+  const unsigned grid = (unsigned)grid64;
+  const bool staged = p.stage_ok != 0;
+  cudaError_t err;
+  if (one_warp)
+    err = staged ? launch_one<T, true, true>(pp, wpb, smem, grid, x_words, s)
+                 : launch_one<T, true, false>(pp, wpb, smem, grid, x_words, s);
+  else
+    err = staged ? launch_one<T, false, true>(pp, wpb, smem, grid, x_words, s)
+                 : launch_one<T, false, false>(pp, wpb, smem, grid, x_words, s);
   if (info) {
     info->grid = (int)grid64;
     info->block = wpb * 32;
     info->traj_per_batch = 32;
     info->smem = smem;
   }
-  return cudaGetLastError();
+  return err;
 }
 
 }  // namespace
+
+bool sparse_supported(int n, int elem_bytes) {
+  if (n < 1) return false;
+  return (elem_bytes == 4 ? sp_per_warp_bytes<float>(n) : sp_per_warp_bytes<double>(n)) <= kMaxSmem;
+}
 
 size_t sparse_ws_words(int n, uint64_t num_tries) {
   // per warp (gw = tl0/32, independent of the CTA shape): N words of transposed best state, and
