@@ -415,31 +415,41 @@ int osa_problem_create_csr_f64(const int32_t *rowptr, const int32_t *col, const 
   step(dev_alloc(&p->d_val64, nnz_a * sizeof(double), p->stream));
   step(dev_alloc(&p->d_diag64, (size_t)n * sizeof(double), p->stream));
   step(dev_alloc(&p->d_val, (nnz_a + (size_t)n) * esz, p->stream));
-  // grouped layout of the sequential sweeps (osa_sparse.cu): groups of four consecutive sites,
-  // entry (t, k) = t-th neighbour of site 4g + k as {byte offset of its spin word, coupling in the
+  // grouped layout of the sequential sweeps (osa_sparse.cu): groups of G consecutive sites,
+  // entry (t, k) = t-th neighbour of site G g + k as {byte offset of its spin word, coupling in the
   // sweep precision}, short rows padded with {offset of the zero word n, 0}; a group is flagged
-  // independent when no coupling joins two of its four sites
-  const int nblk32 = (n + 31) / 32, ngroups = nblk32 * 8;
+  // independent when no coupling joins two of its sites.  G = 8 when at least three quarters of
+  // the 8-groups are independent (random graphs), else 4 (Chimera / Pegasus numbering: the four
+  // qubits of a shore are independent, the eight of a cell are not).
+  const int nblk32 = (n + 31) / 32;
+  auto independent = [&](int i0, int g) {
+    if (i0 + g > n) return false;
+    for (int a = i0; a < i0 + g; ++a)
+      for (int32_t q = rowptr[a]; q < rowptr[a + 1]; ++q)
+        if (col[q] >= i0 && col[q] < i0 + g) return false;
+    return true;
+  };
+  int free8 = 0;
+  for (int i0 = 0; i0 + 8 <= n; i0 += 8) free8 += independent(i0, 8) ? 1 : 0;
+  const int G = (n >= 8 && free8 * 4 >= (n / 8) * 3) ? 8 : 4;
+  p->group = G;
+  const int ngroups = nblk32 * (32 / G);
   std::vector<uint32_t> gbase((size_t)ngroups + 1), ginfo((size_t)ngroups), ent_off;
   std::vector<double> ent_val;
   ent_off.reserve((size_t)nnz + (size_t)n);
   ent_val.reserve((size_t)nnz + (size_t)n);
   for (int g = 0; g < ngroups; ++g) {
-    const int i0 = g * 4;
+    const int i0 = g * G;
     gbase[(size_t)g] = (uint32_t)ent_off.size();
     int len = 0;
-    bool indep = i0 + 4 <= n;
-    for (int a = i0; a < i0 + 4 && a < n; ++a) {
-      len = std::max(len, (int)(rowptr[a + 1] - rowptr[a]));
-      for (int32_t q = rowptr[a]; q < rowptr[a + 1]; ++q)
-        if (col[q] >= i0 && col[q] < i0 + 4) indep = false;
-    }
+    for (int a = i0; a < i0 + G && a < n; ++a) len = std::max(len, (int)(rowptr[a + 1] - rowptr[a]));
+    const bool indep = independent(i0, G);
     if (len > 0xffff) {
       osa_problem_destroy(p);
       return fail(OSA_ERR_UNSUPPORTED, "sparse kernel supports at most 65535 neighbours per site");
     }
     for (int t = 0; t < len; ++t)
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < G; ++k) {
         const int a = i0 + k;
         const bool real = a < n && t < rowptr[a + 1] - rowptr[a];
         ent_off.push_back(real ? (uint32_t)col[rowptr[a] + t] * 4u : (uint32_t)n * 4u);
@@ -449,9 +459,12 @@ int osa_problem_create_csr_f64(const int32_t *rowptr, const int32_t *col, const 
   }
   gbase[(size_t)ngroups] = (uint32_t)ent_off.size();
   p->stage_ok = 1;
+  const int gph = 16 / G;  // groups per staged half block
   for (int h = 0; h < nblk32 * 2; ++h)
-    if (gbase[(size_t)h * 4 + 4] - gbase[(size_t)h * 4] > (uint32_t)SPARSE_HALF_CAP) p->stage_ok = 0;
-  const size_t nent = ent_off.size(), nent_a = nent > 0 ? nent : 1;
+    if (gbase[(size_t)(h + 1) * gph] - gbase[(size_t)h * gph] > (uint32_t)SPARSE_HALF_CAP)
+      p->stage_ok = 0;
+  // 8 entries of slack: the gather requests one row past the end of a group (and drops it)
+  const size_t nent = ent_off.size(), nent_a = nent + 8;
   const size_t ent_bytes = sweep_precision == OSA_SWEEP_F32 ? 8 : 16;
   std::vector<unsigned char> ent(nent_a * ent_bytes, 0);
   for (size_t q = 0; q < nent; ++q) {
@@ -660,6 +673,7 @@ int osa_anneal_traced(osa_problem *p, const double *beta_schedule, const osa_ann
       sp.ginfo = p->d_ginfo;
       sp.gent = p->d_gent;
       sp.stage_ok = p->stage_ok;
+      sp.group = p->group;
       return launch_sparse<T>(sp, p->stream, &info);
     };
     CUDA_TRY(f32 ? run(float()) : run(double()));

@@ -215,10 +215,11 @@ struct SparseParams {
   int nw;
   Counters *counters;
   unsigned long long *trace_hash;  // optional [num_tries], see trace_step()
-  // grouped layout of the sequential sweeps (osa_sparse.cu): groups of four consecutive sites
-  const uint32_t *gbase;  // [8 * ceil(n/32) + 1] first entry of a group
-  const uint32_t *ginfo;  // [8 * ceil(n/32)] len | independent << 16
-  const void *gent;       // SpEnt<T>[gbase[last]]: entry (t, k) of group g at gbase[g] + 4 t + k
+  // grouped layout of the sequential sweeps (osa_sparse.cu): groups of `group` consecutive sites
+  int group;              // 4 or 8
+  const uint32_t *gbase;  // [(32/group) * ceil(n/32) + 1] first entry of a group
+  const uint32_t *ginfo;  // [(32/group) * ceil(n/32)] len | independent << 16
+  const void *gent;       // SpEnt<T>[gbase[last]]: entry (t, k) of group g at gbase[g] + group t + k
   int stage_ok;           // every half block (4 groups) fits the staging buffer
 };
 

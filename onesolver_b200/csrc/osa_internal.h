@@ -29,7 +29,7 @@ struct osa_problem {
   // grouped layout of the sequential sparse sweep (osa_sparse.cu): groups of four sites
   uint32_t *d_gbase = nullptr, *d_ginfo = nullptr;
   unsigned char *d_gent = nullptr;
-  int stage_ok = 0;
+  int stage_ok = 0, group = 4;
   // execution
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};

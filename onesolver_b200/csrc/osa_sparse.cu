@@ -26,14 +26,17 @@ namespace osa {
 namespace {
 
 // Sequential sweeps read the couplings from a GROUPED layout built at problem creation
-// (osa_api.cu, build_sparse_groups): the sites are taken in groups of four consecutive ones; a
-// group stores len x 4 entries, entry (t, k) = the t-th neighbour of site 4g + k as
+// (osa_api.cu): the sites are taken in groups of G = 4 or 8 consecutive ones (8 when at least
+// three quarters of the 8-groups of the instance are independent, see below); a group stores
+// len x G entries, entry (t, k) = the t-th neighbour of site G g + k as
 // {byte offset of its spin word in X, coupling}, rows shorter than the longest of the four padded
 // with {offset of an always-zero word, 0}.  A pad never adds anything (its spin bit is 0), so the
 // additions of a row stay the CSR ones in CSR order.  One 16-byte shared-memory load brings two
-// (fp32) entries, the spin word address needs no arithmetic, and for groups whose four sites are
-// pairwise non-adjacent (flagged at creation) the four fields are independent chains that run
-// side by side: about 4 instructions per neighbour instead of 12 for the plain CSR walk.
+// (fp32) entries, the spin word address needs no index arithmetic, and for groups whose sites are
+// pairwise non-adjacent (flagged at creation) the G fields are independent chains that run side by
+// side and the G decisions are taken together: about 5 instructions per neighbour instead of 12
+// for the plain CSR walk, and G-fold instruction-level parallelism in a kernel whose residency
+// (7-8 warps per SM at N = 5627: the spin words of 32 trajectories take 22.5 KB) cannot hide latency.
 constexpr int SP_LOG = 64;        // flips remembered per trajectory after leaving a best state
 constexpr int SP_HALF_CAP = 256;  // entries per staging buffer: half a block = 16 sites x degree 16
 
@@ -55,7 +58,7 @@ __device__ __forceinline__ uint32_t sp_smem_addr(const void *p) {
 // word of a neighbour is then one load at [offset register + uniform base]); used whenever shared
 // memory, not the 32-CTA limit, bounds the residency.  STAGED: the entries of the next half block
 // are copied into shared memory with cp.async while the current one is processed.
-template <typename T, bool ONE_WARP, bool STAGED>
+template <typename T, int G, bool ONE_WARP, bool STAGED>
 __global__ void k_sparse(const SparseParams<T> p, int x_words_per_warp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using Ent = SpEnt<T>;
@@ -110,7 +113,17 @@ __global__ void k_sparse(const SparseParams<T> p, int x_words_per_warp) {
   // current step's flips) with the logged flips undone
   auto materialize = [&](uint32_t who, bool use_log) {
     if (p.debug_flags & 1) return;
-    for (int j = lane; j < n; j += 32) XB[j] = (XB[j] & ~who) | (X[j] & who);
+    // read-modify-write of the transposed workspace (other lanes' bits stay): eight independent
+    // words in flight per lane -- one by one this loop is a chain of N/32 global round trips
+    int j = lane;
+    for (; j + 7 * 32 < n; j += 8 * 32) {
+      uint32_t w[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) w[u] = XB[j + u * 32];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) XB[j + u * 32] = (w[u] & ~who) | (X[j + u * 32] & who);
+    }
+    for (; j < n; j += 32) XB[j] = (XB[j] & ~who) | (X[j] & who);
     __syncwarp();
     if (use_log && ((who >> lane) & 1u)) {
       for (int e = 0; e < log_len; ++e) atomicXor(&XB[LOG[e * 32 + lane]], 1u << lane);
@@ -145,16 +158,17 @@ __global__ void k_sparse(const SparseParams<T> p, int x_words_per_warp) {
   };
 
   if (p.mode == OSA_MODE_SEQUENTIAL_SWEEP) {
-    // Blocks of 32 sites (one Philox block per 4 sites, one trace update per block), staged in
-    // halves of 16 sites = 4 groups.  Lane l <= 8 holds the entry base of group l of the block
-    // (lane 8: its end), lane l < 8 the group's {len, independent}, lane l the diagonal of site l;
-    // the same for the next block is loaded one block ahead.
+    // Blocks of 32 sites (one Philox block per 4 sites, one trace update per block) = NG groups of
+    // G sites, staged in halves of 16 sites.  Lane l <= NG holds the entry base of group l of the
+    // block (lane NG: its end), lane l < NG the group's {len, independent}, lane l the diagonal of
+    // site l; the same for the next block is loaded one block ahead.
+    constexpr int NG = 32 / G, NGH = NG / 2;
     const int nblk = (n + 31) >> 5;
     const uint32_t lanebit = 1u << lane;
     const Ent *gent = reinterpret_cast<const Ent *>(p.gent);
     auto load_meta = [&](int b, uint32_t &gb, uint32_t &gi, T &dg) {
-      gb = __ldg(p.gbase + b * 8 + min(lane, 8));
-      gi = lane < 8 ? __ldg(p.ginfo + b * 8 + lane) : 0u;
+      gb = __ldg(p.gbase + b * NG + min(lane, NG));
+      gi = lane < NG ? __ldg(p.ginfo + b * NG + lane) : 0u;
       const int i = b * 32 + lane;
       dg = (i < n) ? __ldg(p.diag + i) : (T)0;
     };
@@ -168,23 +182,42 @@ __global__ void k_sparse(const SparseParams<T> p, int x_words_per_warp) {
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    // spin word of a neighbour: X + byte offset
-    auto xword = [&](uint32_t off) {
-      return *reinterpret_cast<const uint32_t *>(reinterpret_cast<const unsigned char *>(X) + off);
+    // Loads of the gather as volatile asm: the compiler keeps them in program order, i.e. BATCHED
+    // (all entries of a row, then all spin words of the row).  Written as plain C++ the loads were
+    // sunk next to their uses and a row became G/2 serial {LDS.128, LDS, FADD} round trips
+    // (profiles/r02/ncu_k_sparse_grouped8_serial_r2e_summary.txt: 58 % of the samples on two
+    // shared-memory latencies per pair of entries).
+    const uint32_t xbase = sp_smem_addr(X);
+    auto xword = [&](uint32_t off) {  // spin word of a neighbour: X + byte offset
+      uint32_t w;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(xbase + off));
+      return w;
     };
-    // four consecutive entries (t, 0..3) / one entry, from the staging buffer or from global memory
-    auto load4 = [&](const Ent *e, Ent (&o)[4]) {
+    auto ld16 = [&](const void *q) {
+      uint4 v;
+      if (STAGED)
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "r"(sp_smem_addr(q)));
+      else
+        asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "l"(q));
+      return v;
+    };
+    // the G entries (t, 0..G-1) of a group / one entry, from the staging buffer or global memory
+    auto load_row = [&](const Ent *e, Ent (&o)[G]) {
       if constexpr (sizeof(T) == 4) {
-        const uint4 a = STAGED ? *reinterpret_cast<const uint4 *>(e) : __ldg(reinterpret_cast<const uint4 *>(e));
-        const uint4 c = STAGED ? *reinterpret_cast<const uint4 *>(e + 2) : __ldg(reinterpret_cast<const uint4 *>(e + 2));
-        o[0].xoff = a.x; o[0].val = __uint_as_float(a.y);
-        o[1].xoff = a.z; o[1].val = __uint_as_float(a.w);
-        o[2].xoff = c.x; o[2].val = __uint_as_float(c.y);
-        o[3].xoff = c.z; o[3].val = __uint_as_float(c.w);
+#pragma unroll
+        for (int k = 0; k < G; k += 2) {
+          const uint4 a = ld16(e + k);
+          o[k].xoff = a.x; o[k].val = __uint_as_float(a.y);
+          o[k + 1].xoff = a.z; o[k + 1].val = __uint_as_float(a.w);
+        }
       } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint4 a = STAGED ? *reinterpret_cast<const uint4 *>(e + k) : __ldg(reinterpret_cast<const uint4 *>(e + k));
+        for (int k = 0; k < G; ++k) {
+          const uint4 a = ld16(e + k);
           o[k].xoff = a.x;
           o[k].val = __hiloint2double((int)a.w, (int)a.z);
         }
@@ -192,10 +225,14 @@ __global__ void k_sparse(const SparseParams<T> p, int x_words_per_warp) {
     };
     auto load1 = [&](const Ent *e, Ent &o) {
       if constexpr (sizeof(T) == 4) {
-        const uint2 a = STAGED ? *reinterpret_cast<const uint2 *>(e) : __ldg(reinterpret_cast<const uint2 *>(e));
+        uint2 a;
+        if (STAGED)
+          asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a.x), "=r"(a.y) : "r"(sp_smem_addr(e)));
+        else
+          asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(a.x), "=r"(a.y) : "l"(e));
         o.xoff = a.x; o.val = __uint_as_float(a.y);
       } else {
-        const uint4 a = STAGED ? *reinterpret_cast<const uint4 *>(e) : __ldg(reinterpret_cast<const uint4 *>(e));
+        const uint4 a = ld16(e);
         o.xoff = a.x;
         o.val = __hiloint2double((int)a.w, (int)a.z);
       }
@@ -204,7 +241,7 @@ __global__ void k_sparse(const SparseParams<T> p, int x_words_per_warp) {
     uint32_t gb, gi, ngb, ngi;
     T dg, ndg;
     load_meta(0, gb, gi, dg);
-    prefetch(__shfl_sync(0xffffffffu, gb, 0), __shfl_sync(0xffffffffu, gb, 4), 0);
+    prefetch(__shfl_sync(0xffffffffu, gb, 0), __shfl_sync(0xffffffffu, gb, NGH), 0);
     unsigned hcount = 0;
     uint32_t step = 0;
     for (int iter = 0; iter < p.num_iter; ++iter) {
@@ -239,54 +276,92 @@ __global__ void k_sparse(const SparseParams<T> p, int x_words_per_warp) {
             const int buf = (int)(hcount & 1u);
             ++hcount;
             // entries of the half after this one: second half of this block / first of the next
-            const uint32_t n0 = hh == 0 ? __shfl_sync(0xffffffffu, gb, 4) : __shfl_sync(0xffffffffu, ngb, 0);
-            const uint32_t n1 = hh == 0 ? __shfl_sync(0xffffffffu, gb, 8) : __shfl_sync(0xffffffffu, ngb, 4);
+            const uint32_t n0 = hh == 0 ? __shfl_sync(0xffffffffu, gb, NGH) : __shfl_sync(0xffffffffu, ngb, 0);
+            const uint32_t n1 = hh == 0 ? __shfl_sync(0xffffffffu, gb, NG) : __shfl_sync(0xffffffffu, ngb, NGH);
             prefetch(n0, n1, buf ^ 1);
             asm volatile("cp.async.wait_group 1;" ::: "memory");  // this half's entries landed
             __syncwarp();
-            const uint32_t h0 = __shfl_sync(0xffffffffu, gb, hh * 4);
+            const uint32_t h0 = __shfl_sync(0xffffffffu, gb, hh * NGH);
 #pragma unroll 1
-            for (int g = hh * 4; g < hh * 4 + 4; ++g) {
-              const int s4 = g * 4;
-              if (s4 >= i_end) break;
-              // one Philox block serves the four sites of the group: their four thresholds (a
-              // chain of ~40 dependent operations each) are computed together so the chains overlap
-              const U4 d = engine_draw(p.seed, traj, STREAM_SEQ, (uint32_t)(b * 32 + s4) >> 2, step);
-              const T th4[4] = {threshold<T>(ts, d.x), threshold<T>(ts, d.y), threshold<T>(ts, d.z),
-                                threshold<T>(ts, d.w)};
+            for (int g = hh * NGH; g < hh * NGH + NGH; ++g) {
+              const int s0 = g * G;
+              if (s0 >= i_end) break;
+              // one Philox block serves four consecutive sites; the thresholds of the whole group
+              // (chains of ~40 dependent operations each) are computed together so that they overlap
+              T th[G];
+#pragma unroll
+              for (int k = 0; k < G; k += 4) {
+                const U4 d = engine_draw(p.seed, traj, STREAM_SEQ, (uint32_t)(b * 32 + s0 + k) >> 2, step);
+                th[k] = threshold<T>(ts, d.x);
+                th[k + 1] = threshold<T>(ts, d.y);
+                th[k + 2] = threshold<T>(ts, d.z);
+                th[k + 3] = threshold<T>(ts, d.w);
+              }
               const uint32_t base = __shfl_sync(0xffffffffu, gb, g);
               const uint32_t info = __shfl_sync(0xffffffffu, gi, g);
               const int len = (int)(info & 0xffffu);
               const Ent *e = STAGED ? stage + buf * SP_HALF_CAP + (base - h0) : gent + base;
               if (info & 0x10000u) {
                 // pairwise non-adjacent sites: none of their flips changes the field of another,
-                // so the four gathers run side by side and the decisions follow in site order
-                T hk[4];
+                // so the G gathers run side by side and the G decisions are taken together
+                T hk[G];
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) hk[k4] = __shfl_sync(0xffffffffu, dg, s4 + k4);
-#pragma unroll 2
+                for (int k = 0; k < G; ++k) hk[k] = __shfl_sync(0xffffffffu, dg, s0 + k);
+                // software pipeline: the entries of row t + 1 are requested before the spin words
+                // of row t (the row after the last one is read and dropped: it lies inside the
+                // staging buffer / the padded entry array)
+                Ent en[G];
+                load_row(e, en);
                 for (int t = 0; t < len; ++t) {
-                  Ent en[4];
-                  load4(e + t * 4, en);
+                  Ent nx[G];
+                  load_row(e + (t + 1) * G, nx);
+                  uint32_t w[G];
 #pragma unroll
-                  for (int k4 = 0; k4 < 4; ++k4)
-                    if (xword(en[k4].xoff) & lanebit) hk[k4] = det::add(hk[k4], en[k4].val);
+                  for (int k = 0; k < G; ++k) w[k] = xword(en[k].xoff);
+#pragma unroll
+                  for (int k = 0; k < G; ++k)
+                    if (w[k] & lanebit) hk[k] = det::add(hk[k], en[k].val);
+#pragma unroll
+                  for (int k = 0; k < G; ++k) en[k] = nx[k];
                 }
+                // a log that could overflow inside this group is written out now (the state before
+                // the group's flips, log undone) -- when it happens does not change any result
+                const uint32_t spill = __ballot_sync(0xffffffffu, !at_best && !mat && log_len > SP_LOG - G);
+                if (spill) {
+                  materialize(spill, true);
+                  if ((spill >> lane) & 1u) mat = true;
+                }
+                uint32_t xiw[G], bal[G];
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) decide(s4 + k4, b * 32 + s4 + k4, hk[k4], th4[k4]);
+                for (int k = 0; k < G; ++k) {
+                  xiw[k] = X[b * 32 + s0 + k];
+                  const T dE = (xiw[k] & lanebit) ? -hk[k] : hk[k];
+                  const bool acc = tv && (dE < th[k]);
+                  if (acc) {
+                    track(b * 32 + s0 + k, dE);
+                    blk_acc |= 1u << (s0 + k);
+                  }
+                  bal[k] = __ballot_sync(0xffffffffu, acc);
+                }
+                __syncwarp();
+                if (lane == 0) {
+#pragma unroll
+                  for (int k = 0; k < G; ++k) X[b * 32 + s0 + k] = xiw[k] ^ bal[k];
+                }
+                __syncwarp();
               } else {
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
-                  const int s = s4 + k4;
+                for (int k = 0; k < G; ++k) {
+                  const int s = s0 + k;
                   if (s >= i_end) break;
                   T hk = __shfl_sync(0xffffffffu, dg, s);
 #pragma unroll 4
                   for (int t = 0; t < len; ++t) {
                     Ent en;
-                    load1(e + t * 4 + k4, en);
+                    load1(e + t * G + k, en);
                     if (xword(en.xoff) & lanebit) hk = det::add(hk, en.val);
                   }
-                  decide(s, b * 32 + s, hk, th4[k4]);
+                  decide(s, b * 32 + s, hk, th[k]);
                 }
               }
             }
@@ -386,14 +461,24 @@ int pick_wpb(size_t per_warp, uint64_t num_tries, int sm_count) {
   return wpb;
 }
 
-template <typename T, bool ONE_WARP, bool STAGED>
+template <typename T, int G, bool ONE_WARP, bool STAGED>
 cudaError_t launch_one(const SparseParams<T> &pp, int wpb, size_t smem, unsigned grid, int x_words,
                        cudaStream_t s) {
-  cudaError_t err = cudaFuncSetAttribute(k_sparse<T, ONE_WARP, STAGED>,
+  cudaError_t err = cudaFuncSetAttribute(k_sparse<T, G, ONE_WARP, STAGED>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
-  k_sparse<T, ONE_WARP, STAGED><<<grid, wpb * 32, smem, s>>>(pp, x_words);
+  k_sparse<T, G, ONE_WARP, STAGED><<<grid, wpb * 32, smem, s>>>(pp, x_words);
   return cudaGetLastError();
+}
+
+template <typename T, int G>
+cudaError_t launch_g(const SparseParams<T> &pp, bool one_warp, bool staged, int wpb, size_t smem,
+                     unsigned grid, int x_words, cudaStream_t s) {
+  if (one_warp)
+    return staged ? launch_one<T, G, true, true>(pp, wpb, smem, grid, x_words, s)
+                  : launch_one<T, G, true, false>(pp, wpb, smem, grid, x_words, s);
+  return staged ? launch_one<T, G, false, true>(pp, wpb, smem, grid, x_words, s)
+                : launch_one<T, G, false, false>(pp, wpb, smem, grid, x_words, s);
 }
 
 template <typename T>
@@ -417,13 +502,10 @@ cudaError_t launch_impl(const SparseParams<T> &p, cudaStream_t s, LaunchInfo *in
   if (grid64 == 0 || grid64 > 0x7fffffffull) return cudaErrorInvalidValue;
   const unsigned grid = (unsigned)grid64;
   const bool staged = p.stage_ok != 0;
-  cudaError_t err;
-  if (one_warp)
-    err = staged ? launch_one<T, true, true>(pp, wpb, smem, grid, x_words, s)
-                 : launch_one<T, true, false>(pp, wpb, smem, grid, x_words, s);
-  else
-    err = staged ? launch_one<T, false, true>(pp, wpb, smem, grid, x_words, s)
-                 : launch_one<T, false, false>(pp, wpb, smem, grid, x_words, s);
+  if (p.group != 4 && p.group != 8) return cudaErrorInvalidValue;
+  const cudaError_t err = p.group == 8
+                              ? launch_g<T, 8>(pp, one_warp, staged, wpb, smem, grid, x_words, s)
+                              : launch_g<T, 4>(pp, one_warp, staged, wpb, smem, grid, x_words, s);
   if (info) {
     info->grid = (int)grid64;
     info->block = wpb * 32;

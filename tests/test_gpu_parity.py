@@ -210,6 +210,9 @@ def test_sharding_by_first_try_is_exact(gpu):
     (128, 6, np.float32, capi.MODE_RANDOM_SITE, 45),
     (517, 15, np.float32, capi.MODE_SEQUENTIAL_SWEEP, 100),
     (517, 15, np.float64, capi.MODE_RANDOM_SITE, 64),
+    # sparse enough for groups of eight sites (osa_api.cu picks G = 8), ragged N, both precisions
+    (3001, 7, np.float64, capi.MODE_SEQUENTIAL_SWEEP, 40),
+    (3001, 7, np.float32, capi.MODE_SEQUENTIAL_SWEEP, 70),
 ])
 def test_sparse_bit_exact(gpu, n, deg, dtype, mode, tries):
     rowptr, col, val, diag = gen.sparse_random_graph(n, deg, seed=n + deg)
