@@ -421,7 +421,13 @@ def run_engine(args):
             "device": device_name(0),
             "entry": "osa_multi_anneal (include/onesolver_b200.h): one process, one host thread and "
                      "stream per GPU, one ncclAllGather of the best records",
-            "nccl": {"comm_nranks_seen": nccl_log_summary(nccl_log), "log": nccl_log or "console"},
+            # comm_devices: size of the communicator the library built (ncclCommInitAll over the
+            # devices of the osa_multi handle; 1 device = no communicator); comm_nranks_seen: the
+            # same number as NCCL's own INFO log states it, when that log went to a file
+            "nccl": {"comm_devices": int(st.get("reserved", 0)) or 1,
+                     "comm_nranks_seen": nccl_log_summary(nccl_log),
+                     "log": nccl_log or ("console (NCCL_DEBUG=%s set by the caller)"
+                                         % os.environ.get("NCCL_DEBUG", "?"))},
             "breakdown_ms_per_step": {"sweep_kernel": agg["ms_sweep"] / args.steps,
                                       "exact_energy_kernel": agg["ms_energy"] / args.steps,
                                       "device_total": agg["ms_total"] / args.steps,

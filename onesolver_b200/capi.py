@@ -108,6 +108,26 @@ class OsaError(RuntimeError):
 _lib = None
 
 
+def _preload_bundled_nccl():
+    """The library binds NCCL at run time by soname (osa_multi.cu), which returns the copy the
+    process already has.  A Python host may import torch LATER, and torch needs the NCCL it was
+    built with (its wheel's nvidia/nccl/lib/libnccl.so.2; the system copy is older and lacks
+    symbols) -- whichever libnccl.so.2 is loaded first wins.  So a Python process loads the bundled
+    copy first, when there is one; torch is not imported for it.  C/C++ hosts without torch simply
+    get the system NCCL."""
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for loc in (spec.submodule_search_locations if spec else []):
+            path = os.path.join(loc, "lib", "libnccl.so.2")
+            if os.path.exists(path):
+                ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL)
+                return path
+    except Exception:  # a missing or unloadable bundled copy is not an error here
+        pass
+    return None
+
+
 def load():
     """Load libonesolver_b200.so; fail loudly when it has not been built."""
     global _lib
@@ -116,6 +136,7 @@ def load():
     if not os.path.exists(LIB_PATH):
         raise OsaError(-1, f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; "
                            "g.build()'` (no CPU fallback exists)")
+    _preload_bundled_nccl()
     lib = ctypes.CDLL(LIB_PATH)
     vp, i32, u64, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_size_t
     P = ctypes.POINTER
