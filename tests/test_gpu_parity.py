@@ -213,6 +213,9 @@ def test_sharding_by_first_try_is_exact(gpu):
     # sparse enough for groups of eight sites (osa_api.cu picks G = 8), ragged N, both precisions
     (3001, 7, np.float64, capi.MODE_SEQUENTIAL_SWEEP, 40),
     (3001, 7, np.float32, capi.MODE_SEQUENTIAL_SWEEP, 70),
+    # degree 40: a half block no longer fits the staging buffer, the entries are read from global memory
+    (300, 40, np.float32, capi.MODE_SEQUENTIAL_SWEEP, 50),
+    (300, 40, np.float64, capi.MODE_SEQUENTIAL_SWEEP, 33),
 ])
 def test_sparse_bit_exact(gpu, n, deg, dtype, mode, tries):
     rowptr, col, val, diag = gen.sparse_random_graph(n, deg, seed=n + deg)
