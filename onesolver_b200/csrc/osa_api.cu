@@ -1102,15 +1102,11 @@ int osa_pa_anneal(osa_problem *p, const double *betas, const osa_pa_params *prm,
     return rc;
   }
   ++launches;
-  std::vector<unsigned char> ts_host(tries * esz);
   for (int step = 0; step < prm->num_steps; ++step) {
     // every replica of every population sweeps at betas[step]
     const double ts64 = prm->accept_rule == OSA_ACCEPT_REFERENCE ? betas[step] : 1.0 / betas[step];
-    for (uint64_t t = 0; t < tries; ++t) {
-      if (f32) ((float *)ts_host.data())[t] = (float)ts64;
-      else ((double *)ts_host.data())[t] = ts64;
-    }
-    PA_TRY(cudaMemcpyAsync(d_ts_traj, ts_host.data(), tries * esz, cudaMemcpyHostToDevice, st));
+    if (f32) PA_TRY(launch_pa_fill<float>((float *)d_ts_traj, (float)ts64, tries, st));
+    else PA_TRY(launch_pa_fill<double>((double *)d_ts_traj, ts64, tries, st));
     auto run = [&](auto tag) -> cudaError_t {
       using T = decltype(tag);
       DenseParams<T> dp{};
@@ -1136,10 +1132,9 @@ int osa_pa_anneal(osa_problem *p, const double *betas, const osa_pa_params *prm,
       return launch_dense_seq_ws<T>(dp, st, &info);
     };
     PA_TRY(f32 ? run(float()) : run(double()));
-    PA_TRY(cudaStreamSynchronize(st));  // ts_host is rewritten by the next step
     // best state of the step against the best kept so far in this slot (e_cur = start energy)
     PA_TRY(launch_pt_track_best(d_ecur, p->d_best_rel, p->d_states, tries, p->nw, d_beste, d_keep, st));
-    launches += 2;
+    launches += 3;
     if (step + 1 == prm->num_steps) break;
     rc = exact_energies(p, d_cur, tries, d_ecur);
     if (rc) {

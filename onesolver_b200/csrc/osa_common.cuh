@@ -275,6 +275,8 @@ cudaError_t launch_pa_resample(uint64_t seed, uint64_t first_pop, uint64_t num_p
                                const double *e_cur, int nw, unsigned long long *cum, uint32_t *nxt,
                                double *e_nxt, int32_t *src_out, unsigned long long *replaced,
                                cudaStream_t s);
+template <typename T>
+cudaError_t launch_pa_fill(T *dst, T value, uint64_t count, cudaStream_t s);
 bool dense_seq_supported(int n, int elem_bytes);
 bool dense_generic_supported(int n, int elem_bytes);
 size_t sparse_ws_words(int n, uint64_t num_tries);

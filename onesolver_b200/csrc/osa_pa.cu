@@ -136,7 +136,24 @@ __global__ void k_pa_resample(uint64_t seed, uint64_t first_pop, uint64_t num_po
   }
 }
 
+template <typename T>
+__global__ void k_pa_fill(T *__restrict__ dst, T value, uint64_t count) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) dst[i] = value;
+}
+
 }  // namespace
+
+// threshold scale of a step for every replica (the resumable sweep kernel takes it per trajectory)
+template <typename T>
+cudaError_t launch_pa_fill(T *dst, T value, uint64_t count, cudaStream_t s) {
+  const uint64_t grid = (count + 255) / 256;
+  if (grid == 0 || grid > 0x7fffffffull) return cudaErrorInvalidValue;
+  k_pa_fill<T><<<(unsigned)grid, 256, 0, s>>>(dst, value, count);
+  return cudaGetLastError();
+}
+template cudaError_t launch_pa_fill<float>(float *, float, uint64_t, cudaStream_t);
+template cudaError_t launch_pa_fill<double>(double *, double, uint64_t, cudaStream_t);
 
 cudaError_t launch_pa_resample(uint64_t seed, uint64_t first_pop, uint64_t num_pops, int M,
                                uint32_t step, double neg_db, const uint32_t *cur,
