@@ -137,3 +137,42 @@ def test_config4_sparse_n5627_65536_tries_linear_schedule(gpu):
         upper = col > rows
         e_ref = x @ diag + ((x[:, rows[upper]] * x[:, col[upper]]) @ val[upper])
         np.testing.assert_allclose(res.best_energies[first:first + 40], e_ref, rtol=REL, atol=1e-9)
+
+
+def test_dense_beyond_the_register_kernel_n10000(gpu):
+    """N = 10000 > 8192: sequential sweeps fall through to the warp-per-trajectory kernel (fields in
+    shared memory); bit-exact against the host replay, energies against the reference formula."""
+    n, tries = 10000, 6
+    q = gen.dense_uniform_qubo(n, seed=77)
+    sched = np.array([12.0, 30.0])
+    with Problem.dense(q, sweep_precision=capi.SWEEP_F32) as prob:
+        res = prob.anneal(sched, 2, tries, mode=capi.MODE_SEQUENTIAL_SWEEP, want_energies=True,
+                          want_states=True, want_trace=True)
+    assert res.stats["kernel_id"] == capi.KID_DENSE_GENERIC
+    with ob.trace(tries) as tr:
+        _, best, _, cnt = ob.replay_dense(q, sched, 2, tries, mode=1, dtype=np.float32, batch_r=1)
+    np.testing.assert_array_equal(res.trace_hash, tr.hashes)
+    np.testing.assert_array_equal(res.best_states_packed, best)
+    assert res.stats["accepts"] == cnt.accepts
+    np.testing.assert_allclose(res.best_energies, ob.energy_packed(q, best), rtol=REL)
+
+
+@pytest.mark.parametrize("n,dtype", [(57000, np.float32), (56000, np.float64)])
+def test_sparse_at_the_largest_supported_size(gpu, n, dtype):
+    """The sparse kernel keeps the spin words of 32 trajectories in shared memory: N up to ~57k.
+    One warp per SM at this size; bit-exact against the host replay, and one site more is refused."""
+    rowptr, col, val, diag = gen.sparse_random_graph(n, 3, seed=n)
+    sched = ob.ref_schedule("linear", 0.1, 2.0, 2)
+    prec = capi.SWEEP_F32 if dtype == np.float32 else capi.SWEEP_F64
+    with Problem.csr(rowptr, col, val, diag, sweep_precision=prec) as prob:
+        res = prob.anneal(sched, 2, 40, mode=capi.MODE_SEQUENTIAL_SWEEP, want_states=True,
+                          want_trace=True)
+    with ob.trace(40) as tr:
+        _, best, _, cnt = ob.replay_csr(rowptr, col, val, diag, sched, 2, 40, mode=1, dtype=dtype)
+    np.testing.assert_array_equal(res.trace_hash, tr.hashes)
+    np.testing.assert_array_equal(res.best_states_packed, best)
+    assert res.stats["accepts"] == cnt.accepts
+    big = 57100 if dtype == np.float32 else 56100
+    rp = np.zeros(big + 1, dtype=np.int32)
+    with pytest.raises(capi.OsaError, match="sparse kernel supports"):
+        Problem.csr(rp, np.zeros(0, dtype=np.int32), np.zeros(0), np.zeros(big), sweep_precision=prec)
