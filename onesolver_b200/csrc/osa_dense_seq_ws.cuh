@@ -17,6 +17,10 @@ constexpr int WS_APPLY_THREADS = 256;
 // so the apply warps get exactly LAUNCH + (LAUNCH - DECIDE) * decide_threads / apply_threads:
 //   DW = 4: 384 threads, 168 -> apply 224 / decide 56   (shapes with >= 192 field registers)
 //   DW = 8: 512 threads, 128 -> apply 200 / decide 56   (small N: the decisions are the bottleneck)
+// (Round 2, profiles/r02/ab_config3_two_ctas.txt: two CTAs per SM -- 384 threads at 80 registers,
+// apply 88 / decide 56, R = 8 or 6 at N = 1024 fp64 -- are 8 % / 18 % slower than one CTA with
+// R = 16: every CTA streams its own rows.  DW has to stay a multiple of 4: setmaxnreg is executed
+// by whole warpgroups, and a decide role of two warps -- half a warpgroup -- hangs the kernel.)
 template <int DW>
 struct WsRegs {
   static constexpr int THREADS = WS_APPLY_THREADS + DW * 32;
