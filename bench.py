@@ -41,9 +41,9 @@ def parse_args():
     # the other GPU configs of BASELINE.json through the same timing harness (not bench lines of
     # the round: they exist so that those shapes can be measured at 1/2/4/8 GPUs as well)
     ap.add_argument("--workload", default="config5",
-                    choices=["config5", "config3", "config4", "random_site"])
+                    choices=["config5", "config3", "config4", "random_site", "config5_f64"])
     ap.add_argument("--no-other-configs", action="store_true",
-                    help="skip the config3 / config4 / random-site sub-records of the headline line")
+                    help="skip the config3 / config4 / random-site / fp64 sub-records of the headline line")
     ap.add_argument("--n", type=int, default=4096)
     ap.add_argument("--tries-per-gpu", type=int, default=131072)
     ap.add_argument("--sweeps", type=int, default=32)
@@ -377,7 +377,7 @@ def run_engine(args):
 
     others = []
     if not args.no_other_configs:
-        for name in ("config3", "config4", "random_site"):
+        for name in ("config3", "config4", "random_site", "config5_f64"):
             others.append(run_sub_record(ranks, args, name, devices))
 
     if ranks.active:
@@ -518,6 +518,22 @@ def other_config_spec(args):
                 "host_input": q, "h2d": q.nbytes + sched.nbytes,
                 "workload": f"BASELINE config 3: dense fp64 N={n} U(-1,1) QUBO, {tries} tries/GPU, "
                             f"{sweeps} sequential sweeps, reference accept rule, geometric beta 0.64->9.6"}
+    if args.workload == "config5_f64":
+        # SURVEY 8(d), C5 secondary: the headline instance and schedule with fp64 fields.  The fp64
+        # copy of Q is 128 MiB -- just above the 126 MB L2 -- and a thread can hold the fields of
+        # 4 trajectories only (R = 4), so a row fetch is shared by 4 instead of 12.
+        n, tries, sweeps = 4096, 16384, 32
+        q = gen.dense_uniform_qubo(n, seed=2024 + 5)
+        sched = construct_geometric_beta_schedule(1.28, 19.2, sweeps)
+        return {"metric": "spin-flip attempts/s, dense N=4096, fp64 fields", "n": n, "tries": tries,
+                "sweeps": sweeps, "sched": sched, "dtype": "f64", "esz": 8,
+                "mode": capi.MODE_SEQUENTIAL_SWEEP,
+                "make": lambda devs, src=q: MultiProblem.dense(src, devices=devs, sweep_precision=capi.SWEEP_F64),
+                "host_input": q, "h2d": q.nbytes + sched.nbytes,
+                "note": "the streamed copy of Q (128 MiB) does not fit the L2 entirely: compare "
+                        "roofline.achieved with MEASURED_PEAKS.json hbm_gbs as well",
+                "workload": f"BASELINE config 5 instance with fp64 fields: dense N={n}, {tries} tries/GPU, "
+                            f"{sweeps} sequential sweeps, reference accept rule, geometric beta 1.28->19.2"}
     if args.workload == "random_site":
         # the reference's loop (annealing.hpp:97-101): one attempt per iteration at a random site
         n, tries, iters = 4096, 16384, 4096
@@ -578,6 +594,11 @@ def sub_record(spec, m, world, steps, warmup, l2_peak, clocks):
                         "algorithmic_bytes_per_launch": alg, "algorithmic_bytes": what, "traffic": None},
            "clocks": clocks, "gpu_launches": agg["launches"],
            "best_energy": m["last"].energy, "best_index": m["last"].index}
+    if "note" in spec:
+        peaks, _ = load_measured_peaks()
+        rec["roofline"]["hbm_peak"] = peaks.get("hbm_gbs")
+        rec["roofline"]["frac_of_hbm_peak"] = alg / sweep_s / 1e9 / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None
+        rec["roofline"]["note"] = spec["note"]
     if "e2e_ms" in m:
         rec["e2e"] = {"value": attempts_per_step / (m["e2e_ms"] / steps * 1e-3), "unit": UNIT,
                       "ms_per_step": m["e2e_ms"] / steps, "h2d_bytes_per_step": int(spec["h2d"]) * world,

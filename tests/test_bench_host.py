@@ -57,6 +57,11 @@ def test_config3_and_config4_specs_match_baseline_shapes():
     assert s4["nnz"] % 2 == 0 and 35000 <= s4["nnz"] // 2 <= 45000  # ~40k couplers, SURVEY 8(d)
     d = np.diff(s4["sched"])
     assert np.allclose(d, d[0])  # linear schedule
+    # the headline instance with fp64 fields (SURVEY 8d, C5 secondary): same instance and schedule
+    s5 = bench.other_config_spec(_args(workload="config5_f64"))
+    assert (s5["n"], s5["sweeps"], s5["dtype"], s5["esz"]) == (4096, 32, "f64", 8)
+    assert np.array_equal(s5["host_input"], bench.make_instance(4096))
+    assert np.allclose(s5["sched"], bench.make_schedule(_args()))
 
 
 def test_reference_arm_of_other_configs_reports_unavailable():
