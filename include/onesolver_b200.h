@@ -147,7 +147,10 @@ int osa_anneal_traced(osa_problem *p, const double *beta_schedule, const osa_ann
  * rounds) exchange configurations with the Metropolis probability computed from exact fp64
  * energies.  Trajectory id = first_group * num_replicas + group * num_replicas + slot; slot k
  * starts on rung k.  Dense problems with n <= 8192 (fp32 sweeps) / 4096 (fp64 sweeps) only.
- * Outputs as in osa_anneal, per trajectory (= per replica slot): the best state each one visited. */
+ * Outputs as in osa_anneal, per trajectory (= per replica slot): the best state each one visited.
+ * The local fields of every replica are carried from round to round in the sweep precision (a
+ * round does not rebuild them from the spins), exactly as one long annealing run carries them;
+ * every exchange decision and every returned energy uses energies recomputed exactly in fp64. */
 typedef struct osa_pt_params {
   uint64_t seed;             /* 1234 like annealing.hpp:87 */
   uint64_t first_group;      /* id offset when a run is sharded over GPUs */
@@ -176,7 +179,9 @@ int osa_pt_anneal(osa_problem *p, const double *betas, const osa_pt_params *para
  * from the Philox stream, so the result does not depend on any reduction order (osa_pa.cu).
  * Trajectory id = (first_population + population) * population_size + slot.  Dense problems with
  * n <= 8192 (fp32 sweeps) / 4096 (fp64 sweeps) only.  Outputs as in osa_anneal, per replica slot:
- * the best state seen in that slot.  stats->pt_swaps = replicas overwritten by a copy of another. */
+ * the best state seen in that slot.  stats->pt_swaps = replicas overwritten by a copy of another.
+ * The local fields travel with a replica through the resampling and are carried from step to
+ * step in the sweep precision; weights and returned energies use exact fp64 energies. */
 typedef struct osa_pa_params {
   uint64_t seed;             /* 1234 like annealing.hpp:87 */
   uint64_t first_population; /* id offset when a run is sharded over GPUs */

@@ -827,12 +827,14 @@ int osa_pt_anneal(osa_problem *p, const double *betas, const osa_pt_params *prm,
   const size_t words = (size_t)tries * p->nw;
   uint32_t *d_cur = nullptr, *d_keep = nullptr;
   double *d_ecur = nullptr, *d_beste = nullptr, *d_dinv = nullptr;
+  char *d_fields = nullptr;  // [tries][ld] local fields carried from round to round
   void *d_ts_traj = nullptr, *d_ts_rung = nullptr;
   int32_t *d_temp_of_slot = nullptr, *d_slot_of_temp = nullptr;
   unsigned long long *d_swaps = nullptr;
   cudaStream_t st = p->stream;
   auto release = [&]() {
     dev_free(d_cur, st);
+    dev_free(d_fields, st);
     dev_free(d_keep, st);
     dev_free(d_ecur, st);
     dev_free(d_beste, st);
@@ -853,6 +855,7 @@ int osa_pt_anneal(osa_problem *p, const double *betas, const osa_pt_params *prm,
     }                                                                                       \
   } while (0)
   PT_TRY(dev_alloc(&d_cur, words * sizeof(uint32_t), st));
+  PT_TRY(dev_alloc(&d_fields, (size_t)tries * p->ld * esz, st));
   PT_TRY(dev_alloc(&d_keep, words * sizeof(uint32_t), st));
   PT_TRY(dev_alloc(&d_ecur, tries * sizeof(double), st));
   PT_TRY(dev_alloc(&d_beste, tries * sizeof(double), st));
@@ -921,6 +924,10 @@ int osa_pt_anneal(osa_problem *p, const double *betas, const osa_pt_params *prm,
       dp.final_states = d_cur;
       dp.tscale_traj = (const T *)d_ts_traj;
       dp.step_base = (uint32_t)round * (uint32_t)prm->sweeps_per_round;
+      // the first round builds the fields from the spins, later rounds continue from what the
+      // round before left (states stay in their slots; only temperatures move)
+      dp.fields_in = round > 0 ? (const T *)d_fields : nullptr;
+      dp.fields_out = (T *)d_fields;
       return launch_dense_seq_ws<T>(dp, st, &info);
     };
     PT_TRY(f32 ? run(float()) : run(double()));
@@ -1051,10 +1058,13 @@ int osa_pa_anneal(osa_problem *p, const double *betas, const osa_pa_params *prm,
   uint32_t *d_cur = nullptr, *d_nxt = nullptr, *d_keep = nullptr;
   double *d_ecur = nullptr, *d_enxt = nullptr, *d_beste = nullptr;
   unsigned long long *d_cum = nullptr, *d_replaced = nullptr;
+  char *d_fields = nullptr, *d_fields_nxt = nullptr;  // [tries][ld] local fields, carried and resampled
   void *d_ts_traj = nullptr;
   cudaStream_t st = p->stream;
   auto release = [&]() {
     dev_free(d_cur, st);
+    dev_free(d_fields, st);
+    dev_free(d_fields_nxt, st);
     dev_free(d_nxt, st);
     dev_free(d_keep, st);
     dev_free(d_ecur, st);
@@ -1075,6 +1085,8 @@ int osa_pa_anneal(osa_problem *p, const double *betas, const osa_pa_params *prm,
   } while (0)
   PA_TRY(dev_alloc(&d_cur, words * sizeof(uint32_t), st));
   PA_TRY(dev_alloc(&d_nxt, words * sizeof(uint32_t), st));
+  PA_TRY(dev_alloc(&d_fields, (size_t)tries * p->ld * esz, st));
+  PA_TRY(dev_alloc(&d_fields_nxt, (size_t)tries * p->ld * esz, st));
   PA_TRY(dev_alloc(&d_keep, words * sizeof(uint32_t), st));
   PA_TRY(dev_alloc(&d_ecur, tries * sizeof(double), st));
   PA_TRY(dev_alloc(&d_enxt, tries * sizeof(double), st));
@@ -1129,6 +1141,10 @@ int osa_pa_anneal(osa_problem *p, const double *betas, const osa_pa_params *prm,
       dp.final_states = d_cur;
       dp.tscale_traj = (const T *)d_ts_traj;
       dp.step_base = (uint32_t)step * (uint32_t)prm->sweeps_per_step;
+      // the first step builds the fields from the spins; later steps continue from the fields of
+      // the replica the slot was resampled from
+      dp.fields_in = step > 0 ? (const T *)d_fields : nullptr;
+      dp.fields_out = (T *)d_fields;
       return launch_dense_seq_ws<T>(dp, st, &info);
     };
     PA_TRY(f32 ? run(float()) : run(double()));
@@ -1147,9 +1163,10 @@ int osa_pa_anneal(osa_problem *p, const double *betas, const osa_pa_params *prm,
         prm->accept_rule == OSA_ACCEPT_REFERENCE ? 1.0 / betas[step + 1] : betas[step + 1];
     PA_TRY(launch_pa_resample(prm->seed, prm->first_population, prm->num_populations, M,
                               (uint32_t)step, -(b1 - b0), d_cur, d_ecur, p->nw, d_cum, d_nxt, d_enxt,
-                              nullptr, d_replaced, st));
+                              nullptr, d_replaced, d_fields, d_fields_nxt, p->ld * esz, st));
     std::swap(d_cur, d_nxt);
     std::swap(d_ecur, d_enxt);
+    std::swap(d_fields, d_fields_nxt);
     launches += 3;
   }
   PA_TRY(cudaEventRecord(p->ev[1], st));

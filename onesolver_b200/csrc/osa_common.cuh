@@ -183,6 +183,12 @@ struct DenseParams {
   const T *tscale_traj;         // [num_tries]: per-trajectory threshold scale, replaces tscale[iter]
   uint32_t *final_states;       // [num_tries][nw]: spins after the last sweep (may alias init_states)
   uint32_t step_base;           // first sweep number of this launch in the STREAM_SEQ counter
+  // local fields carried from launch to launch, [num_tries][ld] in the sweep precision: with
+  // fields_in the launch starts from them instead of rebuilding the fields from the spins (the
+  // rebuild streams every row once: more arithmetic than two sweeps); fields_out receives the
+  // fields after the last sweep (may alias fields_in)
+  const T *fields_in;
+  T *fields_out;
   // optional [num_tries]: FNV-1a hash of the trajectory's accepted flips (osa_anneal_traced)
   unsigned long long *trace_hash;
   // timing experiments only (OSA_WS_DEBUG, tools/probe.py; results are meaningless when set):
@@ -274,6 +280,7 @@ cudaError_t launch_pa_resample(uint64_t seed, uint64_t first_pop, uint64_t num_p
                                uint32_t step, double neg_db, const uint32_t *cur,
                                const double *e_cur, int nw, unsigned long long *cum, uint32_t *nxt,
                                double *e_nxt, int32_t *src_out, unsigned long long *replaced,
+                               const char *fields, char *fields_nxt, size_t field_bytes,
                                cudaStream_t s);
 template <typename T>
 cudaError_t launch_pa_fill(T *dst, T value, uint64_t count, cudaStream_t s);

@@ -83,15 +83,30 @@ __global__ void __launch_bounds__(WsRegs<DW>::THREADS, 1) k_dense_seq_ws(const D
     // =============================== APPLY ROLE ===============================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WsRegs<DW>::APPLY));
     Field<T, CPT> h[R];
+    const bool resume = PT && p.fields_in != nullptr;  // fields of a previous launch (CTA-uniform)
+    if (resume) {
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      T dv[V];
-      const VecT v = *reinterpret_cast<const VecT *>(p.diag + c * CHW + tid * V);
-      vec_unpack<T>(v, dv);
+      for (int r = 0; r < R; ++r) {
+        const T *src = p.fields_in + (batch0 + (uint64_t)(r < nvalid ? r : nvalid - 1)) * p.ld;
 #pragma unroll
-      for (int r = 0; r < R; ++r)
+        for (int c = 0; c < NCH; ++c) {
+          T dv[V];
+          vec_unpack<T>(*reinterpret_cast<const VecT *>(src + c * CHW + tid * V), dv);
 #pragma unroll
-        for (int e = 0; e < V; ++e) h[r].set(c * V + e, dv[e]);
+          for (int e = 0; e < V; ++e) h[r].set(c * V + e, dv[e]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        T dv[V];
+        const VecT v = *reinterpret_cast<const VecT *>(p.diag + c * CHW + tid * V);
+        vec_unpack<T>(v, dv);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int e = 0; e < V; ++e) h[r].set(c * V + e, dv[e]);
+      }
     }
     // snapshot of the 32 columns of block b into sh.snap[par]
     auto snapshot = [&](int b, int par) {
@@ -117,7 +132,7 @@ __global__ void __launch_bounds__(WsRegs<DW>::THREADS, 1) k_dense_seq_ws(const D
     long long t_apply = 0, t_init = clock64();
 
     bar_cta();  // #0: initial spins are in sh.x
-    for (int b = 0; b < nblk; ++b) {
+    for (int b = 0; b < (resume ? 0 : nblk); ++b) {
       uint32_t am[R], sm[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) {
@@ -157,6 +172,21 @@ __global__ void __launch_bounds__(WsRegs<DW>::THREADS, 1) k_dense_seq_ws(const D
         bar_cta();  // B(g+1)
       }
       b = (b + 1 == nblk) ? 0 : b + 1;
+    }
+    if (PT && p.fields_out) {  // the fields after the last sweep, for the next launch
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (r < nvalid) {
+          T *dst = p.fields_out + (batch0 + (uint64_t)r) * p.ld;
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            T dv[V];
+#pragma unroll
+            for (int e = 0; e < V; ++e) dv[e] = h[r].get(c * V + e);
+            *reinterpret_cast<VecT *>(dst + c * CHW + tid * V) = vec_pack<T>(dv);
+          }
+        }
+      }
     }
     if (tid == 0) {
       atomicAdd(&p.counters->row_fetches, cnt_rows);

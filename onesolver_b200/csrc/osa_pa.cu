@@ -98,7 +98,9 @@ __global__ void k_pa_resample(uint64_t seed, uint64_t first_pop, uint64_t num_po
                               uint32_t step, const unsigned long long *__restrict__ cum,
                               const uint32_t *__restrict__ cur, const double *__restrict__ e_cur,
                               int nw, uint32_t *__restrict__ nxt, double *__restrict__ e_nxt,
-                              int32_t *__restrict__ src_out, unsigned long long *replaced) {
+                              int32_t *__restrict__ src_out, unsigned long long *replaced,
+                              const uint4 *__restrict__ fields, uint4 *__restrict__ fields_nxt,
+                              size_t field_vecs) {
   const uint64_t slot = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (slot >= num_pops * (uint64_t)M) return;
@@ -129,6 +131,20 @@ __global__ void k_pa_resample(uint64_t seed, uint64_t first_pop, uint64_t num_po
   }
   const uint64_t from = base + (uint64_t)a;
   for (int k = lane; k < nw; k += 32) nxt[slot * (uint64_t)nw + k] = cur[from * (uint64_t)nw + k];
+  // the local fields travel with the replica (16-byte pieces, eight in flight per lane)
+  if (fields) {
+    const uint4 *src = fields + from * field_vecs;
+    uint4 *dst = fields_nxt + slot * field_vecs;
+    size_t k = lane;
+    for (; k + 7 * 32 < field_vecs; k += 8 * 32) {
+      uint4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = src[k + u * 32];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) dst[k + u * 32] = v[u];
+    }
+    for (; k < field_vecs; k += 32) dst[k] = src[k];
+  }
   if (lane == 0) {
     e_nxt[slot] = e_cur[from];
     if (src_out) src_out[slot] = a;
@@ -159,6 +175,7 @@ cudaError_t launch_pa_resample(uint64_t seed, uint64_t first_pop, uint64_t num_p
                                uint32_t step, double neg_db, const uint32_t *cur,
                                const double *e_cur, int nw, unsigned long long *cum, uint32_t *nxt,
                                double *e_nxt, int32_t *src_out, unsigned long long *replaced,
+                               const char *fields, char *fields_nxt, size_t field_bytes,
                                cudaStream_t s) {
   if (num_pops == 0 || num_pops > 0x7fffffffull) return cudaErrorInvalidValue;
   int threads = 32;
@@ -169,7 +186,9 @@ cudaError_t launch_pa_resample(uint64_t seed, uint64_t first_pop, uint64_t num_p
   const uint64_t grid = (num_pops * (uint64_t)M * 32 + 255) / 256;
   if (grid > 0x7fffffffull) return cudaErrorInvalidValue;
   k_pa_resample<<<(unsigned)grid, 256, 0, s>>>(seed, first_pop, num_pops, M, step, cum, cur, e_cur,
-                                              nw, nxt, e_nxt, src_out, replaced);
+                                              nw, nxt, e_nxt, src_out, replaced,
+                                              reinterpret_cast<const uint4 *>(fields),
+                                              reinterpret_cast<uint4 *>(fields_nxt), field_bytes / 16);
   return cudaGetLastError();
 }
 

@@ -6,7 +6,9 @@ so this restates the engine's own definition (include/onesolver_b200.h, osa_pa_a
 with the oracle's primitives: the bit-exact sweep replay, the reference energy formula, and the
 resampling step orc_pa_resample (integer weights, systematic resampling).  Energies are exact only
 up to summation order, so bit-exact agreement with the GPU is asserted on instances with exactly
-representable coefficients.
+representable coefficients.  (The engine carries the local fields of a replica from round to
+round; this restatement rebuilds them from the spins every round.  The two are the same walk whenever
+every partial sum is exact, which is the case the bit-exact tests use.)
 """
 import numpy as np
 

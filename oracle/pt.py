@@ -5,7 +5,9 @@ recommends one, benchmarks/annealing/performance.md:54-59), so this restates the
 definition (include/onesolver_b200.h, osa_pt_anneal; onesolver_b200/csrc/osa_pt.cu) step by step
 with the oracle's primitives: the bit-exact sweep replay, the reference energy formula, Philox and
 the deterministic -ln(u).  Energies are exact only up to summation order, so bit-exact agreement
-with the GPU is asserted on instances with exactly representable coefficients.
+with the GPU is asserted on instances with exactly representable coefficients.  (The engine carries the local fields of a replica from round to
+round; this restatement rebuilds them from the spins every round.  The two are the same walk whenever
+every partial sum is exact, which is the case the bit-exact tests use.)
 """
 import numpy as np
 
