@@ -100,3 +100,26 @@ def test_python_wrapper_checks_csr_array_lengths():
     with pytest.raises(ValueError):
         Problem.csr(np.array([0, 1], dtype=np.int32), np.array([1], dtype=np.int32), np.array([1.0]),
                     np.zeros(3))
+
+
+def test_headline_kernel_keeps_its_accept_masks_on_the_uniform_datapath():
+    """The dense sweep kernels owe a factor of 3.7 to ptxas keeping the accept masks -- and the
+    +-1/0 multipliers derived from them -- in uniform registers (profiles/r02/
+    ab_one_poller_uniform_datapath_lost.txt: innocuous-looking changes elsewhere in the kernel make
+    it drop them, with bit-identical results).  Pin it on the built library: every packed FMA of the
+    N = 4096 fp32 instantiations takes its multiplier from a uniform register."""
+    import re
+    import shutil
+    import subprocess
+    from onesolver_b200 import capi
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([exe, "-sass", capi.LIB_PATH], capture_output=True, text=True, timeout=600).stdout
+    for kernel, expected in (("k_dense_seq_flowIfLi4ELi12ELi12ELi2ELb0", 192),
+                             ("k_dense_seq_wsIfLi4ELi12ELi12ELi2ELb0ELi4E", 384)):
+        m = re.search(r"Function : \S*" + kernel + r".*?(?=Function : |\Z)", out, re.S)
+        assert m, f"{kernel} not found in the library"
+        fma = re.findall(r"FFMA2 [^;]*;", m.group(0))
+        uniform = [f for f in fma if re.search(r"UR\d+\.F32", f)]
+        assert len(fma) == expected and len(uniform) == len(fma), (kernel, len(fma), len(uniform))
