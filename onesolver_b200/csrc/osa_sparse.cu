@@ -135,7 +135,6 @@ __global__ void k_sparse(const SparseParams<T> p, int x_words_per_warp) {
   auto track = [&](int site, T dE) -> bool {
     const double e = det::add(erel, (double)dE);
     erel = e;
-    ++cnt_acc;
     if (e < best) {
       best = e;
       at_best = true;
@@ -155,6 +154,24 @@ __global__ void k_sparse(const SparseParams<T> p, int x_words_per_warp) {
       return false;
     }
     return true;
+  };
+
+  // the same bookkeeping without branches, for a decision that cannot overflow the log (the
+  // batched path checks that before a group): every lane runs the same ~20 instructions, the lanes
+  // that did not flip keep their state through selects
+  auto track_flat = [&](bool acc, int site, T dE) {
+    const double e = det::add(erel, (double)dE);
+    const bool nb = acc && (e < best);            // new best (strict)
+    const bool leave = acc && !nb && at_best;     // the flip leaves the best state
+    const bool fresh = nb || leave;               // the log restarts
+    const bool do_log = acc && !nb && (leave || !mat);
+    erel = acc ? e : erel;
+    best = nb ? e : best;
+    log_len = fresh ? 0 : log_len;
+    mat = fresh ? false : mat;
+    at_best = nb ? true : (acc ? false : at_best);
+    if (do_log) LOG[log_len * 32 + lane] = (uint16_t)site;
+    log_len += do_log ? 1 : 0;
   };
 
   if (p.mode == OSA_MODE_SEQUENTIAL_SWEEP) {
@@ -337,10 +354,8 @@ __global__ void k_sparse(const SparseParams<T> p, int x_words_per_warp) {
                   xiw[k] = X[b * 32 + s0 + k];
                   const T dE = (xiw[k] & lanebit) ? -hk[k] : hk[k];
                   const bool acc = tv && (dE < th[k]);
-                  if (acc) {
-                    track(b * 32 + s0 + k, dE);
-                    blk_acc |= 1u << (s0 + k);
-                  }
+                  track_flat(acc, b * 32 + s0 + k, dE);
+                  blk_acc |= acc ? (1u << (s0 + k)) : 0u;
                   bal[k] = __ballot_sync(0xffffffffu, acc);
                 }
                 __syncwarp();
@@ -368,6 +383,7 @@ __global__ void k_sparse(const SparseParams<T> p, int x_words_per_warp) {
             __syncwarp();  // everyone is done with stage buffer `buf` before it is refilled
           }
           if (blk_acc != 0u) trace = trace_step(trace, step, (uint32_t)b, blk_acc);
+          cnt_acc += (unsigned)__popc(blk_acc);
           gb = ngb;
           gi = ngi;
           dg = ndg;
@@ -400,6 +416,7 @@ __global__ void k_sparse(const SparseParams<T> p, int x_words_per_warp) {
       }
       __syncwarp();
       if (acc) {
+        ++cnt_acc;
         atomicXor(&X[k], 1u << lane);
         trace = trace_step(trace, (uint32_t)st, (uint32_t)k >> 5, 1u << (k & 31));
       }
