@@ -542,6 +542,7 @@ int osa_problem_destroy(osa_problem *p) {
   dev_free(p->d_states, st);
   dev_free(p->d_xbest_ws, st);
   dev_free(p->d_trace, st);
+  dev_free(p->d_fields, st);
   dev_free(p->d_tscale, st);
   dev_free(p->d_counters, st);
   dev_free(p->d_arg_idx, st);
@@ -644,6 +645,7 @@ int osa_anneal_traced(osa_problem *p, const double *beta_schedule, const osa_ann
 
   LaunchInfo info = {0, 0, 0, 0};
   int launches = 0;
+  int shared_init = 0;  // trajectories per shared row fetch of the initial-field kernel (0: not used)
   CUDA_TRY(cudaEventRecord(p->ev[0], p->stream));
   if (p->sparse) {
     auto run = [&](auto tag) -> cudaError_t {
@@ -697,8 +699,30 @@ int osa_anneal_traced(osa_problem *p, const double *beta_schedule, const osa_ann
       dp.nw = p->nw;
       dp.counters = p->d_counters;
       dp.trace_hash = trace_hash ? p->d_trace : nullptr;
-      return kid == KID_DENSE_SEQ ? launch_dense_seq<T>(dp, p->stream, &info)
-                                  : launch_dense_generic<T>(dp, p->stream, &info);
+      if (kid == KID_DENSE_SEQ) return launch_dense_seq<T>(dp, p->stream, &info);
+      // warp-per-trajectory kernel: the initial fields of all trajectories are built first, with
+      // row fetches shared by a CTA's trajectories (osa_dense_init.cu), when the shape is one the
+      // streaming machinery covers and the field buffer stays within 8 GiB
+      const size_t field_bytes = (size_t)prm->num_tries * p->ld * sizeof(T);
+      // (not below N = 256: the rows of the field buffer are padded to ld >= 1024 floats, and a
+      // trajectory's own build reads N/2 short rows only)
+      if (p->n >= 256 && dense_seq_supported(p->n, (int)sizeof(T)) && field_bytes <= (8ull << 30)) {
+        if (field_bytes > p->cap_fields_bytes) {
+          dev_free(p->d_fields, p->stream);
+          p->d_fields = nullptr;
+          p->cap_fields_bytes = 0;
+          cudaError_t ea = dev_alloc(&p->d_fields, field_bytes, p->stream);
+          if (ea != cudaSuccess) return ea;
+          p->cap_fields_bytes = field_bytes;
+        }
+        dp.fields_out = (T *)p->d_fields;
+        cudaError_t ei = launch_dense_init_fields<T>(dp, p->stream, &shared_init);
+        if (ei != cudaSuccess) return ei;
+        ++launches;
+        dp.fields_in = (const T *)p->d_fields;
+        dp.fields_out = nullptr;
+      }
+      return launch_dense_generic<T>(dp, p->stream, &info);
     };
     CUDA_TRY(f32 ? run(float()) : run(double()));
   }

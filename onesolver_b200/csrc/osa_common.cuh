@@ -263,6 +263,10 @@ template <typename T>
 cudaError_t launch_dense_seq_flow(const DenseParams<T> &p, cudaStream_t s, LaunchInfo *info);
 template <typename T>
 cudaError_t launch_dense_generic(const DenseParams<T> &p, cudaStream_t s, LaunchInfo *info);
+// initial fields of all trajectories into p.fields_out with shared row fetches (osa_dense_init.cu);
+// n within dense_seq_supported.  *traj_per_batch: trajectories that share a fetch.
+template <typename T>
+cudaError_t launch_dense_init_fields(const DenseParams<T> &p, cudaStream_t s, int *traj_per_batch);
 template <typename T>
 cudaError_t launch_sparse(const SparseParams<T> &p, cudaStream_t s, LaunchInfo *info);
 cudaError_t launch_pt_init_states(uint64_t seed, uint64_t first_try, uint64_t num_tries, int n,

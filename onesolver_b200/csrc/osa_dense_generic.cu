@@ -13,6 +13,10 @@
 // exactly.  An accepted flip streams row k of Q (coalesced 16-byte loads) into h.
 #include "osa_common.cuh"
 
+#ifndef OSA_GEN_U
+#define OSA_GEN_U 8  // 16-byte loads of a row in flight per lane (A/B: 16)
+#endif
+
 namespace osa {
 
 namespace {
@@ -43,45 +47,75 @@ __global__ void k_dense_generic(const DenseParams<T> p, int n_pad, int per_warp_
     x[k] = word;
     xb[k] = word;
   }
-  for (int j = lane * V; j < n_pad; j += 32 * V)
-    *reinterpret_cast<VecT *>(h + j) = *reinterpret_cast<const VecT *>(p.diag + j);
+  // fields_in: the initial field of this trajectory, built with shared row fetches by
+  // k_dense_init_fields (osa_dense_init.cu); otherwise it starts at the diagonal and is built below
+  {
+    const T *src = p.fields_in ? p.fields_in + tl * p.ld : p.diag;
+    for (int j = lane * V; j < n_pad; j += 32 * V)
+      *reinterpret_cast<VecT *>(h + j) = *reinterpret_cast<const VecT *>(src + j);
+  }
   __syncwarp();
 
-  // h += sgn * Q[k,:]: 16-byte loads of the row (L2) and of h (shared memory), eight in flight per
-  // lane, 16-byte stores of h
+  // h += sgn * Q[k,:].  The row comes from L2 in 16-byte pieces, U per lane and round; the pieces
+  // of round r+1 are requested BEFORE the arithmetic of round r (two register buffers), so that a
+  // warp always has U..2U loads in flight -- with 13 warps per SM the kernel lives on that.  The
+  // loads are volatile asm: the compiler keeps them in program order (as __ldg they were sunk next
+  // to their uses, three in flight at a time).  h is read and written with 16-byte shared-memory
+  // accesses.
   auto add_row = [&](int k, T sgn) {
     const T *row = p.qoff + (size_t)k * p.ld;
-    constexpr int U = 8;
-    int j = lane * V;
-    for (; j + (U - 1) * 32 * V < n_pad; j += U * 32 * V) {
-      VecT q[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) q[u] = __ldg(reinterpret_cast<const VecT *>(row + j + u * 32 * V));
+    constexpr int U = OSA_GEN_U;
+    constexpr int ROUND = U * 32 * V;  // elements per round and warp
+    auto request = [&](int j0, uint4 (&q)[U]) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
+        const int j = j0 + (u * 32 + lane) * V;
+        if (j < n_pad)
+          asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(q[u].x), "=r"(q[u].y), "=r"(q[u].z), "=r"(q[u].w)
+                       : "l"(row + j));
+      }
+    };
+    auto apply = [&](int j0, const uint4 (&q)[U]) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = j0 + (u * 32 + lane) * V;
+        if (j < n_pad) {
+          T qv[V], hv[V];
+          vec_unpack<T>(*reinterpret_cast<const VecT *>(&q[u]), qv);
+          VecT *hp = reinterpret_cast<VecT *>(h + j);
+          vec_unpack<T>(*hp, hv);
+#pragma unroll
+          for (int e = 0; e < V; ++e) hv[e] = det::fma(sgn, qv[e], hv[e]);
+          *hp = vec_pack<T>(hv);
+        }
+      }
+    };
+    if (n_pad < ROUND) {  // short rows (N < 1024 fp32 / 512 fp64): a plain loop, nothing to pipeline
+      for (int j = lane * V; j < n_pad; j += 32 * V) {
         T qv[V], hv[V];
-        vec_unpack<T>(q[u], qv);
-        VecT *hp = reinterpret_cast<VecT *>(h + j + u * 32 * V);
+        vec_unpack<T>(__ldg(reinterpret_cast<const VecT *>(row + j)), qv);
+        VecT *hp = reinterpret_cast<VecT *>(h + j);
         vec_unpack<T>(*hp, hv);
 #pragma unroll
         for (int e = 0; e < V; ++e) hv[e] = det::fma(sgn, qv[e], hv[e]);
         *hp = vec_pack<T>(hv);
       }
+      return;
     }
-    for (; j < n_pad; j += 32 * V) {
-      T qv[V], hv[V];
-      vec_unpack<T>(__ldg(reinterpret_cast<const VecT *>(row + j)), qv);
-      VecT *hp = reinterpret_cast<VecT *>(h + j);
-      vec_unpack<T>(*hp, hv);
-#pragma unroll
-      for (int e = 0; e < V; ++e) hv[e] = det::fma(sgn, qv[e], hv[e]);
-      *hp = vec_pack<T>(hv);
+    uint4 qa[U], qb[U];
+    request(0, qa);
+    for (int j0 = 0; j0 < n_pad; j0 += 2 * ROUND) {
+      request(j0 + ROUND, qb);  // (no-op past the end of the row)
+      apply(j0, qa);
+      request(j0 + 2 * ROUND, qa);
+      apply(j0 + ROUND, qb);
     }
   };
 
   // initial local field: diag + rows of the set spins, in site order
   unsigned long long cnt_init = 0, cnt_acc = 0;
-  for (int i = 0; i < n; ++i) {
+  for (int i = 0; i < (p.fields_in ? 0 : n); ++i) {
     if ((x[i >> 5] >> (i & 31)) & 1u) {
       add_row(i, (T)1);
       ++cnt_init;

@@ -41,6 +41,8 @@ struct osa_problem {
   size_t cap_states_words = 0;
   uint32_t *d_xbest_ws = nullptr;
   size_t cap_ws_words = 0;
+  char *d_fields = nullptr;  // [tries][ld] initial local fields of the warp-per-trajectory kernel
+  size_t cap_fields_bytes = 0;
   unsigned long long *d_trace = nullptr;  // [cap_trace] flip-trace hashes (osa_anneal_traced)
   size_t cap_trace = 0;
   void *d_tscale = nullptr;

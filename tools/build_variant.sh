@@ -18,7 +18,7 @@ done
 wait
 grep -il " error" "$OUT"/*.ptxas.log && exit 1
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT/libonesolver_b200.so" "$O/osa_api.o" \
-  "$OUT/osa_dense_seq.o" "$OUT/osa_dense_seq_ws.o" "$OUT/osa_dense_seq_ws2.o" "$O/osa_dense_generic.o" "$O/osa_sparse.o" \
+  "$OUT/osa_dense_seq.o" "$OUT/osa_dense_seq_ws.o" "$OUT/osa_dense_seq_ws2.o" "$O/osa_dense_generic.o" "$O/osa_dense_init.o" "$O/osa_sparse.o" \
   "$O/osa_energy.o" "$O/osa_exhaustive.o" "$O/osa_pt.o" "$O/osa_pa.o" "$O/osa_multi.o" -ldl -ccbin /usr/bin/g++
 echo "spills per instantiation (count, ptxas line):"
 grep -h "bytes spill" "$OUT/osa_dense_seq_ws.ptxas.log" "$OUT/osa_dense_seq_ws2.ptxas.log" | sort | uniq -c
