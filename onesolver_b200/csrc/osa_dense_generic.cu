@@ -21,7 +21,10 @@ namespace osa {
 
 namespace {
 
-template <typename T>
+// PIPE: rows of at least one round (U * 32 pieces of 16 bytes) get the software-pipelined row add;
+// the instantiation for shorter rows does not carry its register buffers (64 instead of 127
+// registers: twice the warps per SM where shared memory does not bound the residency anyway)
+template <typename T, bool PIPE>
 __global__ void k_dense_generic(const DenseParams<T> p, int n_pad, int per_warp_bytes) {
   using VecT = typename Vec16<T>::type;
   constexpr int V = Vec16<T>::V;
@@ -91,7 +94,7 @@ __global__ void k_dense_generic(const DenseParams<T> p, int n_pad, int per_warp_
         }
       }
     };
-    if (n_pad < ROUND) {  // short rows (N < 1024 fp32 / 512 fp64): a plain loop, nothing to pipeline
+    if constexpr (!PIPE) {  // short rows (N < 1024 fp32 / 512 fp64): a plain loop, nothing to pipeline
       for (int j = lane * V; j < n_pad; j += 32 * V) {
         T qv[V], hv[V];
         vec_unpack<T>(__ldg(reinterpret_cast<const VecT *>(row + j)), qv);
@@ -101,15 +104,15 @@ __global__ void k_dense_generic(const DenseParams<T> p, int n_pad, int per_warp_
         for (int e = 0; e < V; ++e) hv[e] = det::fma(sgn, qv[e], hv[e]);
         *hp = vec_pack<T>(hv);
       }
-      return;
-    }
-    uint4 qa[U], qb[U];
-    request(0, qa);
-    for (int j0 = 0; j0 < n_pad; j0 += 2 * ROUND) {
-      request(j0 + ROUND, qb);  // (no-op past the end of the row)
-      apply(j0, qa);
-      request(j0 + 2 * ROUND, qa);
-      apply(j0 + ROUND, qb);
+    } else {
+      uint4 qa[U], qb[U];
+      request(0, qa);
+      for (int j0 = 0; j0 < n_pad; j0 += 2 * ROUND) {
+        request(j0 + ROUND, qb);  // (no-op past the end of the row)
+        apply(j0, qa);
+        request(j0 + 2 * ROUND, qa);
+        apply(j0 + ROUND, qb);
+      }
     }
   };
 
@@ -232,13 +235,14 @@ cudaError_t launch_impl(const DenseParams<T> &p, cudaStream_t s, LaunchInfo *inf
   int wpb = (int)(kMaxSmem / pw);
   if (wpb > 4) wpb = 4;  // several small CTAs per SM beat one big one for tiny N
   const size_t smem = pw * (size_t)wpb;
-  cudaError_t err = cudaFuncSetAttribute(k_dense_generic<T>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int n_pad = (p.n + V - 1) / V * V;
+  const bool pipe = n_pad >= OSA_GEN_U * 32 * V;  // at least one round of the pipelined row add
+  auto kern = pipe ? k_dense_generic<T, true> : k_dense_generic<T, false>;
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
   const uint64_t grid64 = (p.num_tries + wpb - 1) / wpb;
   if (grid64 == 0 || grid64 > 0x7fffffffull) return cudaErrorInvalidValue;
-  const int n_pad = (p.n + V - 1) / V * V;
-  k_dense_generic<T><<<(unsigned)grid64, wpb * 32, smem, s>>>(p, n_pad, (int)pw);
+  kern<<<(unsigned)grid64, wpb * 32, smem, s>>>(p, n_pad, (int)pw);
   if (info) {
     info->grid = (int)grid64;
     info->block = wpb * 32;

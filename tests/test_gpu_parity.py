@@ -171,10 +171,13 @@ def test_dense_seq_sweeps_per_beta_and_boltzmann(gpu):
                           accept_rule=capi.ACCEPT_BOLTZMANN)
 
 
+# n = 150: the trajectory builds its own initial field, short rows; 300: initial fields from the
+# shared-fetch kernel (osa_dense_init.cu), short rows; 1100 / 2500: shared initial fields and the
+# software-pipelined row add (one and several rounds, ragged N)
+@pytest.mark.parametrize("n", [150, 300, 1100, 2500])
 @pytest.mark.parametrize("mode", [capi.MODE_RANDOM_SITE, capi.MODE_SEQUENTIAL_SWEEP])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-def test_dense_generic_kernel_bit_exact(gpu, mode, dtype):
-    n = 150
+def test_dense_generic_kernel_bit_exact(gpu, mode, dtype, n):
     q = gen.dense_uniform_qubo(n, seed=11)
     iters = 3 if mode == capi.MODE_SEQUENTIAL_SWEEP else 700
     sched = geo(iters, 0.3, 6.0)
