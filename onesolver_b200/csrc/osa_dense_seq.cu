@@ -312,14 +312,16 @@ static bool use_ws() {
 }
 // ... and of those, the free-running variant (osa_dense_seq_ws2.cu) where it is the faster one:
 // its flip-to-flip decide walk wins in the cold sweeps of a schedule and loses when most sites
-// flip, and a decide warp walks R/4 trajectories side by side.  Measured on the bench schedule
-// (profiles/r02/flow_check4_parity_and_probes.txt): N = 4096 fp32 (R = 12) 0.453 against 0.444 of
-// the L2 roofline, the R = 16 shapes (N <= 2048) 10-25 % slower.  OSA_WS_FLOW=0/1 forces one of
-// the two for A/B runs; both give the same results bit for bit.
+// flip, and it has no CTA barrier per block.  Measured per shape on a bench-like schedule
+// (profiles/r02/flow_shapes_probe.txt, flow_check4_parity_and_probes.txt): the shapes with
+// R <= 12 trajectories per CTA gain 6 % (fp32 N = 5120, fp64 N = 1536 / 2048) to 29 % (fp64
+// N = 4096, R = 4), fp32 N = 4096 gains 2.6 % on the bench; the R = 16 shapes (fp32 N <= 2048,
+// fp64 N <= 1024) lose 5-16 % and fp32 N = 3072 loses 3 %, so they keep the lock-step kernel.
+// OSA_WS_FLOW=0/1 forces one of the two for A/B runs; both give the same results bit for bit.
 static bool use_flow(size_t ld, int elem_bytes) {
   const char *e = getenv("OSA_WS_FLOW");
   if (e) return e[0] != '0';
-  return elem_bytes == 4 && ld == 4096;
+  return elem_bytes == 4 ? ld >= 4096 : ld >= 1536;
 }
 template <typename T>
 static cudaError_t launch_ws_any(const DenseParams<T> &p, cudaStream_t s, LaunchInfo *info) {

@@ -401,7 +401,8 @@ def test_cli_csr_route(gpu, tmp_path):
 
 
 @pytest.mark.parametrize("n,dtype,tries", [(200, np.float32, 30), (1100, np.float32, 17),
-                                           (513, np.float64, 20), (4096, np.float32, 13)])
+                                           (513, np.float64, 20), (4096, np.float32, 13),
+                                           (2048, np.float64, 9), (5000, np.float32, 9)])
 def test_single_role_kernel_is_bit_identical_to_warp_specialised(gpu, monkeypatch, n, dtype, tries):
     """OSA_DS_WS=0 selects k_dense_seq (decide and apply back to back); the default k_dense_seq_ws
     overlaps them.  Both must walk exactly the trajectories of the host replay."""
@@ -410,8 +411,12 @@ def test_single_role_kernel_is_bit_identical_to_warp_specialised(gpu, monkeypatc
     sched = geo(3, 0.02 * scale, 0.6 * scale)
     a, _ = run_and_compare_dense(q, sched, 3, tries, capi.MODE_SEQUENTIAL_SWEEP, dtype)
     # the other warp-specialised variant (lock-step roles <-> free-running roles): the default
-    # picks the free-running kernel for N = 4096 fp32 only (osa_dense_seq.cu, use_flow)
-    monkeypatch.setenv("OSA_WS_FLOW", "0" if (n == 4096 and dtype == np.float32) else "1")
+    # picks the free-running kernel for fp32 rows of >= 4096 and fp64 rows of >= 1536 elements
+    # (osa_dense_seq.cu, use_flow)
+    unit = 1024 if dtype == np.float32 else 512
+    ld = -(-n // unit) * unit
+    default_is_flow = ld >= (4096 if dtype == np.float32 else 1536)
+    monkeypatch.setenv("OSA_WS_FLOW", "0" if default_is_flow else "1")
     c, _ = run_and_compare_dense(q, sched, 3, tries, capi.MODE_SEQUENTIAL_SWEEP, dtype)
     monkeypatch.delenv("OSA_WS_FLOW")
     monkeypatch.setenv("OSA_DS_WS", "0")
