@@ -593,7 +593,16 @@ cudaError_t launch_dense_seq_flow<float>(const DenseParams<float> &p, cudaStream
     case 2: return launch_flow<float, 2, 16, 16, 4>(p, s, info);
     case 3: return launch_flow<float, 3, 12, 12, 4>(p, s, info);
 #endif
-    case 4: return launch_flow<float, 4, 12, 12, 2>(p, s, info);
+    case 4: {
+      const char *e = getenv("OSA_FLOW_R");  // tuning knob (result-preserving): trajectories per CTA
+      const int r = e ? atoi(e) : 12;
+#ifndef OSA_WS_ONLY_F32_4
+      if (r == 8) return launch_flow<float, 4, 8, 12, 2>(p, s, info);
+      if (r == 10) return launch_flow<float, 4, 10, 12, 2>(p, s, info);
+      if (r == 6) return launch_flow<float, 4, 6, 12, 2>(p, s, info);
+#endif
+      return launch_flow<float, 4, 12, 12, 2>(p, s, info);
+    }
 #ifndef OSA_WS_ONLY_F32_4
     case 5: return launch_flow<float, 5, 8, 9, 2>(p, s, info);
     case 6: return launch_flow<float, 6, 8, 8, 2>(p, s, info);
