@@ -41,7 +41,7 @@ def parse_args():
     # the other GPU configs of BASELINE.json through the same timing harness (not bench lines of
     # the round: they exist so that those shapes can be measured at 1/2/4/8 GPUs as well)
     ap.add_argument("--workload", default="config5",
-                    choices=["config5", "config3", "config4", "random_site", "config5_f64"])
+                    choices=["config5", "config3", "config4", "random_site", "config5_f64", "config5_r8"])
     ap.add_argument("--no-other-configs", action="store_true",
                     help="skip the config3 / config4 / random-site / fp64 sub-records of the headline line")
     ap.add_argument("--n", type=int, default=4096)
@@ -377,7 +377,7 @@ def run_engine(args):
 
     others = []
     if not args.no_other_configs:
-        for name in ("config3", "config4", "random_site", "config5_f64"):
+        for name in ("config3", "config4", "random_site", "config5_f64", "config5_r8"):
             others.append(run_sub_record(ranks, args, name, devices))
 
     if ranks.active:
@@ -534,6 +534,21 @@ def other_config_spec(args):
                         "roofline.achieved with MEASURED_PEAKS.json hbm_gbs as well",
                 "workload": f"BASELINE config 5 instance with fp64 fields: dense N={n}, {tries} tries/GPU, "
                             f"{sweeps} sequential sweeps, reference accept rule, geometric beta 1.28->19.2"}
+    if args.workload == "config5_r8":
+        # the headline workload on fewer trajectories, with R = 8 instead of 12 trajectories sharing a
+        # row fetch (OSA_FLOW_R, a result-preserving knob of the free-running kernel): the rows go by
+        # faster (higher roofline fraction) and each serves fewer attempts (lower throughput) --
+        # the trade-off behind the headline line's roofline.frac, measured by the driver as well
+        n, tries, sweeps = 4096, 32768, 32
+        q = gen.dense_uniform_qubo(n, seed=2024 + 5)
+        sched = construct_geometric_beta_schedule(1.28, 19.2, sweeps)
+        return {"metric": "spin-flip attempts/s, dense N=4096, 8 trajectories per row fetch", "n": n,
+                "tries": tries, "sweeps": sweeps, "sched": sched, "dtype": "f32", "esz": 4,
+                "mode": capi.MODE_SEQUENTIAL_SWEEP, "env": {"OSA_FLOW_R": "8"},
+                "make": lambda devs, src=q: MultiProblem.dense(src, devices=devs, sweep_precision=capi.SWEEP_F32),
+                "host_input": q, "h2d": q.nbytes + sched.nbytes,
+                "workload": f"headline instance and schedule, {tries} tries/GPU, R = 8 trajectories per "
+                            f"CTA instead of 12 (OSA_FLOW_R=8): roofline fraction against throughput"}
     if args.workload == "random_site":
         # the reference's loop (annealing.hpp:97-101): one attempt per iteration at a random site
         n, tries, iters = 4096, 16384, 4096
@@ -619,8 +634,13 @@ def run_sub_record(ranks, args, name, devices):
     if ranks.active:
         sampler.start()
         make = lambda: spec["make"](devices)  # noqa: E731
-        m = measure(ranks, make, spec["sched"], spec["sweeps"], spec["tries"] * world, 1, 1,
-                    spec["mode"], None if args.no_e2e else make)
+        os.environ.update(spec.get("env", {}))
+        try:
+            m = measure(ranks, make, spec["sched"], spec["sweeps"], spec["tries"] * world, 1, 1,
+                        spec["mode"], None if args.no_e2e else make)
+        finally:
+            for k in spec.get("env", {}):
+                os.environ.pop(k, None)
         clocks = sampler.stop()
         from onesolver_b200 import measure_read_bandwidth
         l2_peak = max(measure_read_bandwidth(64 << 20, 64, device=0) for _ in range(3))
@@ -651,6 +671,7 @@ def run_other_config(args):
     if ranks.active:
         sampler.start()
         make = lambda: spec["make"](devices)  # noqa: E731
+        os.environ.update(spec.get("env", {}))
         m = measure(ranks, make, spec["sched"], spec["sweeps"], spec["tries"] * world, args.steps,
                     args.warmup, spec["mode"], None if args.no_e2e else make)
         clocks = sampler.stop()
