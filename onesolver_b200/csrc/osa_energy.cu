@@ -218,6 +218,77 @@ __global__ void k_energy_csr(const int32_t *__restrict__ rowptr, const int32_t *
   out[t] = e;
 }
 
+// The same sums with 32 states per warp (lane = state): the packed states of the warp are staged
+// transposed in shared memory (word k of lane l at X[k * 32 + l], conflict-free), the CSR row of a
+// site is read once per warp (broadcast loads) instead of once per state, and the loads of four
+// entries -- column, value, spin word -- are requested together (volatile asm: kept in that order)
+// in front of the four dependent additions.  Per state the additions are the ones of k_energy_csr
+// in the same order, so the two kernels return the same bits.
+__global__ void k_energy_csr_ms(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                                const double *__restrict__ val64, const double *__restrict__ diag64,
+                                int n, const uint32_t *__restrict__ states, int nw, uint64_t count,
+                                double *__restrict__ out) {
+  extern __shared__ uint32_t s_words[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t t = ((uint64_t)blockIdx.x * (blockDim.x >> 5) + warp) * 32ull + lane;
+  const bool valid = t < count;
+  uint32_t *X = s_words + (size_t)warp * nw * 32;
+  for (int k = 0; k < nw; ++k) X[k * 32 + lane] = valid ? states[t * (uint64_t)nw + k] : 0u;
+  __syncwarp();
+  const uint32_t xbase = (uint32_t)__cvta_generic_to_shared(X) + 4u * (uint32_t)lane;
+  auto ldg_i32 = [](const int32_t *p) {
+    int v;
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+  };
+  auto ldg_f64 = [](const double *p) {
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+  };
+  auto lds_word = [&](int c) {  // this lane's word that holds spin c
+    uint32_t w;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(xbase + 128u * (uint32_t)(c >> 5)));
+    return w;
+  };
+  double e = 0.0;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const uint32_t wi = X[(i0 >> 5) * 32 + lane];
+    const int iend = min(32, n - i0);
+    // row bounds of the block's sites: lane s holds those of site i0 + s
+    const int rp_lo = __ldg(rowptr + min(i0 + lane, n)), rp_hi = __ldg(rowptr + min(i0 + lane + 1, n));
+    const double dg = (i0 + lane < n) ? __ldg(diag64 + i0 + lane) : 0.0;
+    for (int s = 0; s < iend; ++s) {
+      const bool xi = (wi >> s) & 1u;
+      const int q0 = __shfl_sync(0xffffffffu, rp_lo, s), q1 = __shfl_sync(0xffffffffu, rp_hi, s);
+      const double di = __shfl_sync(0xffffffffu, dg, s);
+      if (!__any_sync(0xffffffffu, xi)) continue;  // warp-uniform
+      const int i = i0 + s;
+      if (xi) e += di;
+      int q = q0;
+      for (; q + 4 <= q1; q += 4) {
+        int c[4];
+        double v[4];
+        uint32_t w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) c[u] = ldg_i32(col + q + u);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ldg_f64(val64 + q + u);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) w[u] = lds_word(c[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (c[u] > i && xi && ((w[u] >> (c[u] & 31)) & 1u)) e += v[u];
+      }
+      for (; q < q1; ++q) {
+        const int c = ldg_i32(col + q);
+        if (c > i && xi && ((lds_word(c) >> (c & 31)) & 1u)) e += ldg_f64(val64 + q);
+      }
+    }
+  }
+  if (valid) out[t] = e;
+}
+
 __global__ void __launch_bounds__(1024) k_argmin(const double *__restrict__ e, uint64_t count,
                                                  unsigned long long *out_idx, double *out_e) {
   __shared__ double s_e[32];
@@ -322,6 +393,21 @@ cudaError_t launch_energy_csr(const int32_t *rowptr, const int32_t *col, const d
                               const double *diag64, int n, const uint32_t *states, int nw,
                               uint64_t count, double *out, cudaStream_t s) {
   if (count == 0) return cudaSuccess;
+  // 32 states per warp while their packed words fit in shared memory (N up to ~28k), else one
+  // state per thread (OSA_ENERGY_CSR_SCALAR=1 forces it: A/B and the equality test)
+  const size_t per_warp = (size_t)nw * 32 * sizeof(uint32_t);
+  if (per_warp <= 112 * 1024 && !getenv("OSA_ENERGY_CSR_SCALAR")) {
+    int wpb = (int)((112 * 1024) / per_warp);
+    if (wpb > 4) wpb = 4;
+    const size_t smem = per_warp * (size_t)wpb;
+    cudaError_t err = cudaFuncSetAttribute(k_energy_csr_ms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    const uint64_t warps = (count + 31) / 32;
+    const uint64_t grid = (warps + wpb - 1) / wpb;
+    if (grid > 0x7fffffffull) return cudaErrorInvalidValue;
+    k_energy_csr_ms<<<(unsigned)grid, wpb * 32, smem, s>>>(rowptr, col, val64, diag64, n, states, nw, count, out);
+    return cudaGetLastError();
+  }
   const uint64_t grid = (count + 127) / 128;
   if (grid > 0x7fffffffull) return cudaErrorInvalidValue;
   k_energy_csr<<<(unsigned)grid, 128, 0, s>>>(rowptr, col, val64, diag64, n, states, nw, count,

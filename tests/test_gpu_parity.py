@@ -426,3 +426,23 @@ def test_single_role_kernel_is_bit_identical_to_warp_specialised(gpu, monkeypatc
     np.testing.assert_array_equal(a.trace_hash, b.trace_hash)
     np.testing.assert_array_equal(a.trace_hash, c.trace_hash)
     assert a.stats["grid"] != 0 and b.stats["grid"] != 0
+
+
+def test_csr_energy_kernels_agree_bit_for_bit(gpu, monkeypatch):
+    """Exact fp64 energies on a CSR problem: 32 states per warp (staged transposed in shared memory,
+    a site's CSR row read once per warp) against one state per thread (OSA_ENERGY_CSR_SCALAR=1) --
+    the same additions in the same order, so the same bits, and both equal to the reference formula
+    to rounding."""
+    for n, deg in ((1500, 11), (77, 5), (3001, 3)):
+        rowptr, col, val, diag = gen.sparse_random_graph(n, deg, seed=77 + n)
+        rng = np.random.default_rng(3)
+        states = pack_states(rng.integers(0, 2, size=(333, n)).astype(np.uint8))
+        with Problem.csr(rowptr, col, val, diag) as prob:
+            monkeypatch.delenv("OSA_ENERGY_CSR_SCALAR", raising=False)
+            a = prob.energy_batch(states)
+            monkeypatch.setenv("OSA_ENERGY_CSR_SCALAR", "1")
+            b = prob.energy_batch(states)
+        monkeypatch.delenv("OSA_ENERGY_CSR_SCALAR", raising=False)
+        np.testing.assert_array_equal(a, b)
+        q = gen.csr_to_dense(rowptr, col, val, diag)
+        np.testing.assert_allclose(a, ob.energy_packed(q, states), rtol=REL, atol=1e-9)
