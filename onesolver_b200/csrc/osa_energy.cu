@@ -219,33 +219,32 @@ __global__ void k_energy_csr(const int32_t *__restrict__ rowptr, const int32_t *
 }
 
 // The same sums with 32 states per warp (lane = state): the packed states of the warp are staged
-// transposed in shared memory (word k of lane l at X[k * 32 + l], conflict-free), the CSR row of a
-// site is read once per warp (broadcast loads) instead of once per state, and the loads of four
-// entries -- column, value, spin word -- are requested together (volatile asm: kept in that order)
-// in front of the four dependent additions.  Per state the additions are the ones of k_energy_csr
-// in the same order, so the two kernels return the same bits.
+// transposed in shared memory (word k of lane l at X[k * 32 + l], conflict-free); the CSR entries of
+// a block of 32 sites are brought into shared memory with one coalesced pass (the arrays are 1 MB:
+// they do not stay in the L1 left next to the staged states, and read entry by entry every load
+// was an L2 round trip), so a site's row is read once per warp from shared memory, and the loads
+// of four entries -- column, value, spin word -- are requested together (volatile asm: kept in that
+// order) in front of the four dependent additions.  Per state the additions are the ones of
+// k_energy_csr in the same order, so the two kernels return the same bits.
+constexpr int ECSR_CAP = 512;  // staged entries per block of 32 sites; larger blocks read global memory
+
 __global__ void k_energy_csr_ms(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                                 const double *__restrict__ val64, const double *__restrict__ diag64,
                                 int n, const uint32_t *__restrict__ states, int nw, uint64_t count,
                                 double *__restrict__ out) {
-  extern __shared__ uint32_t s_words[];
+  extern __shared__ __align__(16) unsigned char s_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint64_t t = ((uint64_t)blockIdx.x * (blockDim.x >> 5) + warp) * 32ull + lane;
   const bool valid = t < count;
-  uint32_t *X = s_words + (size_t)warp * nw * 32;
+  const size_t per_warp = (size_t)ECSR_CAP * 12 + (size_t)nw * 128;
+  unsigned char *mine = s_raw + (size_t)warp * per_warp;
+  double *sv = reinterpret_cast<double *>(mine);                       // [ECSR_CAP] values
+  int32_t *sc = reinterpret_cast<int32_t *>(mine + ECSR_CAP * 8);      // [ECSR_CAP] columns
+  uint32_t *X = reinterpret_cast<uint32_t *>(mine + ECSR_CAP * 12);    // [nw][32] spin words
   for (int k = 0; k < nw; ++k) X[k * 32 + lane] = valid ? states[t * (uint64_t)nw + k] : 0u;
   __syncwarp();
   const uint32_t xbase = (uint32_t)__cvta_generic_to_shared(X) + 4u * (uint32_t)lane;
-  auto ldg_i32 = [](const int32_t *p) {
-    int v;
-    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-  };
-  auto ldg_f64 = [](const double *p) {
-    double v;
-    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    return v;
-  };
+  const uint32_t cbase = (uint32_t)__cvta_generic_to_shared(sc), vbase = (uint32_t)__cvta_generic_to_shared(sv);
   auto lds_word = [&](int c) {  // this lane's word that holds spin c
     uint32_t w;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(xbase + 128u * (uint32_t)(c >> 5)));
@@ -258,6 +257,16 @@ __global__ void k_energy_csr_ms(const int32_t *__restrict__ rowptr, const int32_
     // row bounds of the block's sites: lane s holds those of site i0 + s
     const int rp_lo = __ldg(rowptr + min(i0 + lane, n)), rp_hi = __ldg(rowptr + min(i0 + lane + 1, n));
     const double dg = (i0 + lane < n) ? __ldg(diag64 + i0 + lane) : 0.0;
+    const int e0 = __shfl_sync(0xffffffffu, rp_lo, 0), e1 = __shfl_sync(0xffffffffu, rp_hi, iend - 1);
+    const bool staged = e1 - e0 <= ECSR_CAP;
+    __syncwarp();  // the previous block's entries are no longer read
+    if (staged) {
+      for (int q = e0 + lane; q < e1; q += 32) {
+        sc[q - e0] = __ldg(col + q);
+        sv[q - e0] = __ldg(val64 + q);
+      }
+    }
+    __syncwarp();
     for (int s = 0; s < iend; ++s) {
       const bool xi = (wi >> s) & 1u;
       const int q0 = __shfl_sync(0xffffffffu, rp_lo, s), q1 = __shfl_sync(0xffffffffu, rp_hi, s);
@@ -266,23 +275,32 @@ __global__ void k_energy_csr_ms(const int32_t *__restrict__ rowptr, const int32_
       const int i = i0 + s;
       if (xi) e += di;
       int q = q0;
-      for (; q + 4 <= q1; q += 4) {
-        int c[4];
-        double v[4];
-        uint32_t w[4];
+      if (staged) {
+        for (; q + 4 <= q1; q += 4) {
+          int c[4];
+          double v[4];
+          uint32_t w[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) c[u] = ldg_i32(col + q + u);
+          for (int u = 0; u < 4; ++u)
+            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(c[u]) : "r"(cbase + 4u * (uint32_t)(q - e0 + u)));
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = ldg_f64(val64 + q + u);
+          for (int u = 0; u < 4; ++u)
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v[u]) : "r"(vbase + 8u * (uint32_t)(q - e0 + u)));
 #pragma unroll
-        for (int u = 0; u < 4; ++u) w[u] = lds_word(c[u]);
+          for (int u = 0; u < 4; ++u) w[u] = lds_word(c[u]);
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (c[u] > i && xi && ((w[u] >> (c[u] & 31)) & 1u)) e += v[u];
-      }
-      for (; q < q1; ++q) {
-        const int c = ldg_i32(col + q);
-        if (c > i && xi && ((lds_word(c) >> (c & 31)) & 1u)) e += ldg_f64(val64 + q);
+          for (int u = 0; u < 4; ++u)
+            if (c[u] > i && xi && ((w[u] >> (c[u] & 31)) & 1u)) e += v[u];
+        }
+        for (; q < q1; ++q) {
+          const int c = sc[q - e0];
+          if (c > i && xi && ((lds_word(c) >> (c & 31)) & 1u)) e += sv[q - e0];
+        }
+      } else {
+        for (; q < q1; ++q) {
+          const int c = __ldg(col + q);
+          if (c > i && xi && ((lds_word(c) >> (c & 31)) & 1u)) e += __ldg(val64 + q);
+        }
       }
     }
   }
@@ -395,7 +413,7 @@ cudaError_t launch_energy_csr(const int32_t *rowptr, const int32_t *col, const d
   if (count == 0) return cudaSuccess;
   // 32 states per warp while their packed words fit in shared memory (N up to ~28k), else one
   // state per thread (OSA_ENERGY_CSR_SCALAR=1 forces it: A/B and the equality test)
-  const size_t per_warp = (size_t)nw * 32 * sizeof(uint32_t);
+  const size_t per_warp = (size_t)nw * 32 * sizeof(uint32_t) + (size_t)ECSR_CAP * 12;
   if (per_warp <= 112 * 1024 && !getenv("OSA_ENERGY_CSR_SCALAR")) {
     int wpb = (int)((112 * 1024) / per_warp);
     if (wpb > 4) wpb = 4;
