@@ -173,8 +173,10 @@ def test_dense_seq_sweeps_per_beta_and_boltzmann(gpu):
 
 # n = 150: the trajectory builds its own initial field, short rows; 300: initial fields from the
 # shared-fetch kernel (osa_dense_init.cu), short rows; 1100 / 2500: shared initial fields and the
-# software-pipelined row add (one and several rounds, ragged N)
-@pytest.mark.parametrize("n", [150, 300, 1100, 2500])
+# software-pipelined row add (one and several rounds, ragged N); 2500 in fp64 and 4100 in both
+# precisions: rows of 16 KiB and more, the rows of a batch's accepted flips are added in one pass
+# over the fields while the walk follows them through gathered elements (ragged last piece)
+@pytest.mark.parametrize("n", [150, 300, 1100, 2500, 4100])
 @pytest.mark.parametrize("mode", [capi.MODE_RANDOM_SITE, capi.MODE_SEQUENTIAL_SWEEP])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_dense_generic_kernel_bit_exact(gpu, mode, dtype, n):
