@@ -133,6 +133,14 @@ __global__ void k_dense_generic(const DenseParams<T> p, int n_pad, int per_warp_
   // of the NEXT row (or the next piece of the first row) as soon as its value is consumed, so the
   // stream never drains between rows.  The loads are volatile asm: the compiler keeps them in
   // program order (as __ldg they were sunk next to their uses, three in flight at a time).
+  // (ptxas issues the U refills of an item together and waits for them at the next item.)
+  // Measured and rejected, all bit-exact (profiles/r02/ab_random_site_batched_rows_variants.txt):
+  // refills in groups of 2 / 4 loads (-9 %), U = 6 / 10 / 12 / 16 (-14 % ... -52 %), two alternating
+  // buffers with an unpredicated path for whole pieces (55 instead of 181 warp instructions per item:
+  // -3 %, rejected_random_site_two_buffers_r3s.patch), a 13th warp per SM (+0.1 %), and walking
+  // batch b+1 while the rows of batch b stream (-16 %, rejected_random_site_walk_ahead_r3p.patch).
+  // The kernel moves 15.3 TB/s through the L2 at 96 % hits (ncu, 66 % of the lts peak) whatever is
+  // done to its instruction stream.
   auto add_rows = [&](int cnt, int myk, T mysgn) {
     {
       constexpr int U = OSA_GEN_U;

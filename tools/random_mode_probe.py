@@ -1,5 +1,5 @@
 """Throughput of the reference-faithful random-site mode (k_dense_generic / k_sparse) on the GPU."""
-import sys, json
+import os, sys, json
 sys.path.insert(0, ".")
 import numpy as np
 from onesolver_b200 import Problem, capi
@@ -8,8 +8,10 @@ from onesolver_b200 import problems as gen
 def geo(n, lo, hi):
     return lo * (hi / lo) ** (np.arange(n) / max(1, n - 1))
 
-for n, tries, iters, prec in ((4096, 8192, 8192, capi.SWEEP_F32), (1024, 16384, 8192, capi.SWEEP_F64),
-                              (128, 65536, 4096, capi.SWEEP_F64)):
+cases = ((4096, 8192, 8192, capi.SWEEP_F32), (1024, 16384, 8192, capi.SWEEP_F64), (128, 65536, 4096, capi.SWEEP_F64))
+if os.environ.get("TRIES"):  # N = 4096 only, with a trajectory count that fills whole waves
+    cases = ((4096, int(os.environ["TRIES"]), int(os.environ.get("ITERS", 2048)), capi.SWEEP_F32),)
+for n, tries, iters, prec in cases:
     q = gen.dense_uniform_qubo(n, seed=2024)
     s = np.sqrt(n)
     with Problem.dense(q, sweep_precision=prec) as p:
