@@ -623,12 +623,18 @@ def sub_record(spec, m, world, steps, warmup, l2_peak, clocks):
     return rec
 
 
+SUB_RECORD_STEPS = {"config3": 1, "config4": 2, "random_site": 5, "config5_f64": 2, "config5_r8": 2}
+
+
 def run_sub_record(ranks, args, name, devices):
-    """A reduced-step measurement of another workload inside the headline run (W = 1, K = 1)."""
+    """A reduced-step measurement of another workload inside the headline run: W = 3 warm-up
+    steps; K = 1 for the 1.5 s step of config 3, 2 for the 0.4-0.6 s steps, 5 for the 55 ms step of
+    the random-site loop (its host-side share of the end-to-end step is not a single sample then)."""
     import copy
     a = copy.copy(args)
     a.workload = name
     world = len(devices)
+    k, w = SUB_RECORD_STEPS[name], 3
     spec = other_config_spec(a) if ranks.active else None
     sampler = ClockSampler(devices)
     if ranks.active:
@@ -636,7 +642,7 @@ def run_sub_record(ranks, args, name, devices):
         make = lambda: spec["make"](devices)  # noqa: E731
         os.environ.update(spec.get("env", {}))
         try:
-            m = measure(ranks, make, spec["sched"], spec["sweeps"], spec["tries"] * world, 1, 1,
+            m = measure(ranks, make, spec["sched"], spec["sweeps"], spec["tries"] * world, k, w,
                         spec["mode"], None if args.no_e2e else make)
         finally:
             for k in spec.get("env", {}):
@@ -644,8 +650,8 @@ def run_sub_record(ranks, args, name, devices):
         clocks = sampler.stop()
         from onesolver_b200 import measure_read_bandwidth
         l2_peak = max(measure_read_bandwidth(64 << 20, 64, device=0) for _ in range(3))
-        return sub_record(spec, m, world, 1, 1, l2_peak, clocks)
-    measure(ranks, None, None, 0, 0, 1, 1, 0, None if args.no_e2e else (lambda: None))
+        return sub_record(spec, m, world, k, w, l2_peak, clocks)
+    measure(ranks, None, None, 0, 0, k, w, 0, None if args.no_e2e else (lambda: None))
     return None
 
 
