@@ -634,7 +634,7 @@ def run_sub_record(ranks, args, name, devices):
     a = copy.copy(args)
     a.workload = name
     world = len(devices)
-    k, w = SUB_RECORD_STEPS[name], 3
+    nsteps, nwarm = SUB_RECORD_STEPS[name], 3
     spec = other_config_spec(a) if ranks.active else None
     sampler = ClockSampler(devices)
     if ranks.active:
@@ -642,7 +642,7 @@ def run_sub_record(ranks, args, name, devices):
         make = lambda: spec["make"](devices)  # noqa: E731
         os.environ.update(spec.get("env", {}))
         try:
-            m = measure(ranks, make, spec["sched"], spec["sweeps"], spec["tries"] * world, k, w,
+            m = measure(ranks, make, spec["sched"], spec["sweeps"], spec["tries"] * world, nsteps, nwarm,
                         spec["mode"], None if args.no_e2e else make)
         finally:
             for k in spec.get("env", {}):
@@ -650,8 +650,8 @@ def run_sub_record(ranks, args, name, devices):
         clocks = sampler.stop()
         from onesolver_b200 import measure_read_bandwidth
         l2_peak = max(measure_read_bandwidth(64 << 20, 64, device=0) for _ in range(3))
-        return sub_record(spec, m, world, k, w, l2_peak, clocks)
-    measure(ranks, None, None, 0, 0, k, w, 0, None if args.no_e2e else (lambda: None))
+        return sub_record(spec, m, world, nsteps, nwarm, l2_peak, clocks)
+    measure(ranks, None, None, 0, 0, nsteps, nwarm, 0, None if args.no_e2e else (lambda: None))
     return None
 
 
