@@ -316,7 +316,11 @@ def measure(ranks, make_problem, sched, sweeps, total_tries, steps, warmup, mode
             with e2e_make() as p2:  # host arrays -> device layouts on every GPU, every step
                 p2.anneal(sched, sweeps, total_tries, mode=mode, want_energies=True)
         if ranks.active:
-            e2e_step()  # warm-up (allocator, communicator)
+            # warm-up (communicator; the library's memory pool needs up to three create / anneal /
+            # destroy cycles before it stops growing: a 250 ms stall in cycle 3 of the random-site
+            # workload, tools/e2e_random_probe.py)
+            for _ in range(max(1, min(3, warmup))):
+                e2e_step()
         ranks.barrier()
         t1 = time.perf_counter()
         if ranks.active:
