@@ -123,3 +123,8 @@ def test_headline_kernel_keeps_its_accept_masks_on_the_uniform_datapath():
         fma = re.findall(r"FFMA2 [^;]*;", m.group(0))
         uniform = [f for f in fma if re.search(r"UR\d+\.F32", f)]
         assert len(fma) == expected and len(uniform) == len(fma), (kernel, len(fma), len(uniform))
+    # the warp-per-trajectory kernel has its three forms in both precisions: short rows, pipelined
+    # flip-by-flip row add, rows of a batch added in one pass (osa_dense_generic.cu)
+    for t in "fd":
+        for form in ("Lb0ELb0E", "Lb1ELb0E", "Lb1ELb1E"):
+            assert re.search(r"Function : \S*k_dense_genericI" + t + form, out), (t, form)
