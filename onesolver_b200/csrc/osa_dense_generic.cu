@@ -17,6 +17,8 @@
 // memory once, takes the rows in flip order (so every element sees the same fma sequence as with
 // one pass per row) and is written back once, and the 16-byte loads of consecutive rows follow
 // each other without a drain in between.
+#include <cstdlib>
+
 #include "osa_common.cuh"
 
 #ifndef OSA_GEN_U
@@ -30,10 +32,11 @@ namespace {
 // PIPE: rows of at least one round (U * 32 pieces of 16 bytes) get the software-pipelined row add;
 // the instantiation for shorter rows does not carry its register buffers (64 instead of 127
 // registers: twice the warps per SM where shared memory does not bound the residency anyway)
-// BATCH (rows of at least four rounds, 16 KiB): the rows of all accepted flips of a batch are
-// added in one pass over h (add_rows below); shorter rows are added flip by flip -- a warp then has
-// its whole row in flight at once, and the gathered element per lane and flip costs more than the
-// saved shared-memory passes (measured: N = 4096 fp32 +33 %, N = 1024 fp64 -28 %)
+// BATCH: the rows of all accepted flips of a batch are added in one pass over h (add_rows below);
+// otherwise they are added flip by flip -- a warp then has up to two rounds of its row in flight,
+// and the gathered element per lane and flip costs more than the saved shared-memory passes
+// unless many warps share the SM (launch_impl chooses; measured: N = 4096 fp32 +33 %, N = 1024
+// fp64 -28 %)
 template <typename T, bool PIPE, bool BATCH>
 __global__ void k_dense_generic(const DenseParams<T> p, int n_pad, int per_warp_bytes) {
   using VecT = typename Vec16<T>::type;
@@ -386,7 +389,15 @@ cudaError_t launch_impl(const DenseParams<T> &p, cudaStream_t s, LaunchInfo *inf
   const size_t smem = pw * (size_t)wpb;
   const int n_pad = (p.n + V - 1) / V * V;
   const bool pipe = n_pad >= OSA_GEN_U * 32 * V;  // at least one round of the pipelined row add
-  const bool batch = n_pad >= 4 * OSA_GEN_U * 32 * V;  // rows of 16 KiB and more
+  // rows added batch by batch: where it measured faster -- fp32 rows of 16 to 20 KiB (N = 4096 ...
+  // 5120: +33 % at 4096), where 11 or more warps per SM hide a walk that waits for one gathered
+  // element per flip.  Longer rows leave fewer warps (N = 6000: -4 %, 8192: -20 %), and fp64 fields
+  // lose whatever the row length (N = 2048: -25 %, 4096: -53 %;
+  // profiles/r02/ab_random_site_batched_rows_variants.txt).  OSA_GEN_BATCH = 0 / 1 forces the choice
+  // for rows of at least four rounds (result-preserving; tests run both forms).
+  bool batch = sizeof(T) == 4 && n_pad >= 4 * OSA_GEN_U * 32 * V && n_pad <= 5 * OSA_GEN_U * 32 * V;
+  if (const char *e = getenv("OSA_GEN_BATCH"))
+    batch = atoi(e) != 0 && n_pad >= 4 * OSA_GEN_U * 32 * V;
   auto kern = batch ? k_dense_generic<T, true, true>
                     : pipe ? k_dense_generic<T, true, false> : k_dense_generic<T, false, false>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -173,9 +173,9 @@ def test_dense_seq_sweeps_per_beta_and_boltzmann(gpu):
 
 # n = 150: the trajectory builds its own initial field, short rows; 300: initial fields from the
 # shared-fetch kernel (osa_dense_init.cu), short rows; 1100 / 2500: shared initial fields and the
-# software-pipelined row add (one and several rounds, ragged N); 2500 in fp64 and 4100 in both
-# precisions: rows of 16 KiB and more, the rows of a batch's accepted flips are added in one pass
-# over the fields while the walk follows them through gathered elements (ragged last piece)
+# software-pipelined row add (one and several rounds, ragged N); 4100 in fp32: the rows of a
+# batch's accepted flips are added in one pass over the fields while the walk follows them through
+# gathered elements (ragged last piece)
 @pytest.mark.parametrize("n", [150, 300, 1100, 2500, 4100])
 @pytest.mark.parametrize("mode", [capi.MODE_RANDOM_SITE, capi.MODE_SEQUENTIAL_SWEEP])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
@@ -184,6 +184,20 @@ def test_dense_generic_kernel_bit_exact(gpu, mode, dtype, n):
     iters = 3 if mode == capi.MODE_SEQUENTIAL_SWEEP else 700
     sched = geo(iters, 0.3, 6.0)
     res, _ = run_and_compare_dense(q, sched, iters, 37, mode, dtype, kernel=capi.KID_DENSE_GENERIC)
+    assert res.stats["kernel_id"] == capi.KID_DENSE_GENERIC
+
+
+# rows of at least four rounds: both forms of the row add, whatever the library would choose
+# (OSA_GEN_BATCH; the batched form is the default for fp32 rows of 16-20 KiB only)
+@pytest.mark.parametrize("force", ["0", "1"])
+@pytest.mark.parametrize("n,dtype", [(2500, np.float64), (4100, np.float32), (4100, np.float64),
+                                     (6100, np.float32)])
+def test_dense_generic_row_add_forms_bit_exact(gpu, monkeypatch, force, n, dtype):
+    monkeypatch.setenv("OSA_GEN_BATCH", force)
+    q = gen.dense_uniform_qubo(n, seed=12)
+    sched = geo(500, 0.3, 6.0)
+    res, _ = run_and_compare_dense(q, sched, 500, 21, capi.MODE_RANDOM_SITE, dtype,
+                                   kernel=capi.KID_DENSE_GENERIC)
     assert res.stats["kernel_id"] == capi.KID_DENSE_GENERIC
 
 

@@ -11,6 +11,9 @@ def geo(n, lo, hi):
 cases = ((4096, 8192, 8192, capi.SWEEP_F32), (1024, 16384, 8192, capi.SWEEP_F64), (128, 65536, 4096, capi.SWEEP_F64))
 if os.environ.get("TRIES"):  # N = 4096 only, with a trajectory count that fills whole waves
     cases = ((4096, int(os.environ["TRIES"]), int(os.environ.get("ITERS", 2048)), capi.SWEEP_F32),)
+if os.environ.get("CASES"):  # "n:tries:iters:f32|f64,..."
+    cases = tuple((int(a), int(b), int(c), capi.SWEEP_F32 if d == "f32" else capi.SWEEP_F64)
+                  for a, b, c, d in (x.split(":") for x in os.environ["CASES"].split(",")))
 for n, tries, iters, prec in cases:
     q = gen.dense_uniform_qubo(n, seed=2024)
     s = np.sqrt(n)
