@@ -213,11 +213,17 @@ int create_dense(const TIn *qsym, int n, int device, int prec, osa_problem **out
   } while (0)
 
   const size_t total = (size_t)n * n;
-  TRY_B(dev_alloc(&d_in, total * sizeof(TIn), p->stream));
-  TRY_B(dev_alloc(&d_bad, sizeof(int), p->stream));
+  // The upload buffer is released at the end of this function: it is allocated AFTER the arrays
+  // that stay, so that the hole it leaves lies at the end of what the pool has handed out.
+  // Allocated first, the hole sat in front of the resident arrays, the 268 MB of shared initial
+  // fields of a random-site anneal did not fit it, and in a create / anneal / destroy loop the
+  // pool re-mapped its memory every cycle (3-50 ms per allocation, one of a full second:
+  // tools/pool_probe.cu, profiles/r02/pool_probe_allocation_order.txt).
   TRY_B(dev_alloc(&p->d_qoff, p->rows_pad * p->ld * esz, p->stream));
   TRY_B(dev_alloc(&p->d_diag, p->ld * esz, p->stream));
   TRY_B(dev_alloc(&p->d_q64, p->rows_pad * p->ld64 * sizeof(double), p->stream));
+  TRY_B(dev_alloc(&d_in, total * sizeof(TIn), p->stream));
+  TRY_B(dev_alloc(&d_bad, sizeof(int), p->stream));
   TRY_B(cudaMemcpyAsync(d_in, qsym, total * sizeof(TIn), cudaMemcpyHostToDevice, p->stream));
   TRY_B(cudaMemsetAsync(d_bad, 0, sizeof(int), p->stream));
   TRY_B(cudaMemsetAsync(p->d_qoff, 0, p->rows_pad * p->ld * esz, p->stream));
