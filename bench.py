@@ -316,9 +316,9 @@ def measure(ranks, make_problem, sched, sweeps, total_tries, steps, warmup, mode
             with e2e_make() as p2:  # host arrays -> device layouts on every GPU, every step
                 p2.anneal(sched, sweeps, total_tries, mode=mode, want_energies=True)
         if ranks.active:
-            # warm-up (communicator; the library's memory pool needs up to three create / anneal /
-            # destroy cycles before it stops growing: a 250 ms stall in cycle 3 of the random-site
-            # workload, tools/e2e_random_probe.py)
+            # warm-up cycles (communicator, memory pool: the first create allocates device memory,
+            # later ones reuse it -- osa_api.cu allocates the upload buffer after the resident
+            # arrays so that the pool does not re-map from cycle to cycle, tools/pool_probe.cu)
             for _ in range(max(1, min(3, warmup))):
                 e2e_step()
         ranks.barrier()
@@ -648,8 +648,7 @@ def run_sub_record(ranks, args, name, devices):
         if not args.no_e2e:
             e2e_make = make
             if spec.get("host_input") is not None:
-                # like the headline: the step's input lives in pinned host memory (a pageable
-                # 134 MB upload stalls for 250 ms now and then, tools/e2e_random_probe.py)
+                # like the headline: the step's input lives in pinned host memory
                 from onesolver_b200 import pinned_copy
                 q_pinned, free_pinned = pinned_copy(spec["host_input"])
                 e2e_make = lambda: spec["make"](devices, q_pinned)  # noqa: E731
