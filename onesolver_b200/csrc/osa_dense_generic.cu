@@ -17,6 +17,7 @@
 // memory once, takes the rows in flip order (so every element sees the same fma sequence as with
 // one pass per row) and is written back once, and the 16-byte loads of consecutive rows follow
 // each other without a drain in between.
+#include <algorithm>
 #include <cstdlib>
 
 #include "osa_common.cuh"
@@ -384,9 +385,6 @@ cudaError_t launch_impl(const DenseParams<T> &p, cudaStream_t s, LaunchInfo *inf
   constexpr int V = Vec16<T>::V;
   const size_t pw = per_warp_bytes<T>(p.n);
   if (pw > kMaxSmem) return cudaErrorInvalidValue;
-  int wpb = (int)(kMaxSmem / pw);
-  if (wpb > 4) wpb = 4;  // several small CTAs per SM beat one big one for tiny N
-  const size_t smem = pw * (size_t)wpb;
   const int n_pad = (p.n + V - 1) / V * V;
   const bool pipe = n_pad >= OSA_GEN_U * 32 * V;  // at least one round of the pipelined row add
   // rows added batch by batch: where it measured faster -- fp32 rows of 16 to 20 KiB (N = 4096 ...
@@ -400,8 +398,29 @@ cudaError_t launch_impl(const DenseParams<T> &p, cudaStream_t s, LaunchInfo *inf
     batch = atoi(e) != 0 && n_pad >= 4 * OSA_GEN_U * 32 * V;
   auto kern = batch ? k_dense_generic<T, true, true>
                     : pipe ? k_dense_generic<T, true, false> : k_dense_generic<T, false, false>;
-  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // CTA size: at most four warps (several small CTAs per SM beat one big one for tiny N), and of
+  // the sizes 4 ... 1 the one that keeps most warps resident -- the warps of a CTA do not interact,
+  // and with fields of 32 KiB per warp (N = 4096 fp64, 8192 fp32) a four-warp CTA left room for
+  // one CTA = 4 warps per SM where 6 fit.  OSA_GEN_WPB forces a size (result-preserving).
+  int wpb = (int)std::min<size_t>(4, kMaxSmem / pw);
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(pw * (size_t)wpb));
   if (err != cudaSuccess) return err;
+  {
+    int best_warps = 0, best_wpb = wpb;
+    for (int w = wpb; w >= 1; --w) {
+      int ctas = 0;
+      err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, w * 32, pw * (size_t)w);
+      if (err != cudaSuccess) return err;
+      if (ctas * w > best_warps) best_warps = ctas * w, best_wpb = w;
+    }
+    wpb = best_wpb;
+    if (const char *e = getenv("OSA_GEN_WPB")) {
+      const int w = atoi(e);
+      if (w >= 1 && w <= 4 && (size_t)w * pw <= kMaxSmem) wpb = w;
+    }
+  }
+  const size_t smem = pw * (size_t)wpb;
   const uint64_t grid64 = (p.num_tries + wpb - 1) / wpb;
   if (grid64 == 0 || grid64 > 0x7fffffffull) return cudaErrorInvalidValue;
   kern<<<(unsigned)grid64, wpb * 32, smem, s>>>(p, n_pad, (int)pw);
