@@ -106,3 +106,52 @@ def test_committed_round_bench_lines_carry_the_contract_keys():
         assert ENGINE_KEYS <= set(line) and line["n_gpus"] == n and line["scaling"] == "weak"
         # whole-job aggregate: close to n times the one-GPU value of the same round
         assert 0.9 * n * 8.9e9 < line["value"] < 1.1 * n * one["value"]
+
+
+def test_sub_records_pass_their_step_counts(monkeypatch):
+    """Every sub-record of the headline line has a step count, and run_sub_record hands K / W to the
+    measurement and to the record unchanged (the env-variable loop of a spec once overwrote K)."""
+    import onesolver_b200
+    names = ("config3", "config4", "random_site", "config5_f64", "config5_r8")
+    assert set(bench.SUB_RECORD_STEPS) == set(names)
+    seen = {}
+
+    class Ranks:
+        active = True
+
+    class Sampler:
+        def __init__(self, devices):
+            pass
+
+        def start(self):
+            pass
+
+        def stop(self):
+            return {"sm_mhz": 0}
+
+    def fake_spec(a):
+        return {"make": lambda devs, src=None: ("problem", src), "sched": [1.0], "sweeps": 1, "tries": 7,
+                "mode": 0, "env": {"OSA_FLOW_R": "8"}, "host_input": np.zeros((2, 2))}
+
+    def fake_measure(ranks, make, sched, sweeps, tries, steps, warmup, mode, e2e_make=None):
+        seen["measure"] = (steps, warmup, tries)
+        seen["env_inside"] = os.environ.get("OSA_FLOW_R")
+        seen["e2e_src"] = e2e_make()[1] if e2e_make else None
+        return {"m": 1}
+
+    def fake_record(spec, m, world, steps, warmup, l2_peak, clocks):
+        return {"steps": steps, "warmup": warmup}
+
+    monkeypatch.setattr(bench, "other_config_spec", fake_spec)
+    monkeypatch.setattr(bench, "measure", fake_measure)
+    monkeypatch.setattr(bench, "sub_record", fake_record)
+    monkeypatch.setattr(bench, "ClockSampler", Sampler)
+    monkeypatch.setattr(onesolver_b200, "measure_read_bandwidth", lambda *a, **k: 1.0)
+    monkeypatch.setattr(onesolver_b200, "pinned_copy", lambda q: ("pinned", lambda: seen.setdefault("freed", True)))
+    monkeypatch.delenv("OSA_FLOW_R", raising=False)
+    for name in names:
+        rec = bench.run_sub_record(Ranks(), _args(no_e2e=False), name, [0, 1])
+        k = bench.SUB_RECORD_STEPS[name]
+        assert rec == {"steps": k, "warmup": 3} and seen["measure"] == (k, 3, 14)
+        assert seen["env_inside"] == "8" and "OSA_FLOW_R" not in os.environ
+        assert seen["e2e_src"] == "pinned" and seen.pop("freed")
