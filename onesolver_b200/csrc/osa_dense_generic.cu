@@ -146,53 +146,51 @@ __global__ void k_dense_generic(const DenseParams<T> p, int n_pad, int per_warp_
   // The kernel moves 15.3 TB/s through the L2 at 96 % hits (ncu, 66 % of the lts peak) whatever is
   // done to its instruction stream.
   auto add_rows = [&](int cnt, int myk, T mysgn) {
+    constexpr int U = OSA_GEN_U;
+    constexpr int ROUND = U * 32 * V;  // elements per piece and warp
+    uint4 q[U];
+    auto request = [&](const T *at, int j0, int u) {
+      const int j = j0 + (u * 32 + lane) * V;
+      if (j < n_pad)
+        asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(q[u].x), "=r"(q[u].y), "=r"(q[u].z), "=r"(q[u].w)
+                     : "l"(at + j));
+    };
+    T sgn = __shfl_sync(0xffffffffu, mysgn, 0);
     {
-      constexpr int U = OSA_GEN_U;
-      constexpr int ROUND = U * 32 * V;  // elements per piece and warp
-      uint4 q[U];
-      auto request = [&](const T *at, int j0, int u) {
+      const T *row = p.qoff + (size_t)__shfl_sync(0xffffffffu, myk, 0) * p.ld;
+#pragma unroll
+      for (int u = 0; u < U; ++u) request(row, 0, u);
+    }
+    for (int j0 = 0; j0 < n_pad; j0 += ROUND) {
+      T hv[U][V];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
         const int j = j0 + (u * 32 + lane) * V;
-        if (j < n_pad)
-          asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
-                       : "=r"(q[u].x), "=r"(q[u].y), "=r"(q[u].z), "=r"(q[u].w)
-                       : "l"(at + j));
-      };
-      T sgn = __shfl_sync(0xffffffffu, mysgn, 0);
-      {
-        const T *row = p.qoff + (size_t)__shfl_sync(0xffffffffu, myk, 0) * p.ld;
-#pragma unroll
-        for (int u = 0; u < U; ++u) request(row, 0, u);
+        if (j < n_pad) vec_unpack<T>(*reinterpret_cast<const VecT *>(h + j), hv[u]);
       }
-      for (int j0 = 0; j0 < n_pad; j0 += ROUND) {
-        T hv[U][V];
+      for (int i = 0; i < cnt; ++i) {
+        const bool last = i + 1 == cnt;
+        const int ni = last ? 0 : i + 1;
+        const int nj0 = last ? j0 + ROUND : j0;
+        const T *nrow = p.qoff + (size_t)__shfl_sync(0xffffffffu, myk, ni) * p.ld;
+        const T nsgn = __shfl_sync(0xffffffffu, mysgn, ni);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int j = j0 + (u * 32 + lane) * V;
-          if (j < n_pad) vec_unpack<T>(*reinterpret_cast<const VecT *>(h + j), hv[u]);
-        }
-        for (int i = 0; i < cnt; ++i) {
-          const bool last = i + 1 == cnt;
-          const int ni = last ? 0 : i + 1;
-          const int nj0 = last ? j0 + ROUND : j0;
-          const T *nrow = p.qoff + (size_t)__shfl_sync(0xffffffffu, myk, ni) * p.ld;
-          const T nsgn = __shfl_sync(0xffffffffu, mysgn, ni);
+          T qv[V];
+          vec_unpack<T>(*reinterpret_cast<const VecT *>(&q[u]), qv);
+          request(nrow, nj0, u);  // refill: same piece of the next row / next piece of row 0
+          if (j0 + (u * 32 + lane) * V < n_pad) {
 #pragma unroll
-          for (int u = 0; u < U; ++u) {
-            T qv[V];
-            vec_unpack<T>(*reinterpret_cast<const VecT *>(&q[u]), qv);
-            request(nrow, nj0, u);  // refill: same piece of the next row / next piece of row 0
-            if (j0 + (u * 32 + lane) * V < n_pad) {
-#pragma unroll
-              for (int e = 0; e < V; ++e) hv[u][e] = det::fma(sgn, qv[e], hv[u][e]);
-            }
+            for (int e = 0; e < V; ++e) hv[u][e] = det::fma(sgn, qv[e], hv[u][e]);
           }
-          sgn = nsgn;
         }
+        sgn = nsgn;
+      }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int j = j0 + (u * 32 + lane) * V;
-          if (j < n_pad) *reinterpret_cast<VecT *>(h + j) = vec_pack<T>(hv[u]);
-        }
+      for (int u = 0; u < U; ++u) {
+        const int j = j0 + (u * 32 + lane) * V;
+        if (j < n_pad) *reinterpret_cast<VecT *>(h + j) = vec_pack<T>(hv[u]);
       }
     }
   };
